@@ -1,0 +1,291 @@
+// km_api.cu -- the C-ABI of include/kmanip_b200.h: handle management, buffers, launches.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "km_launch.cuh"
+
+namespace km {
+KmVtable vtable_solo_arm_f32();
+KmVtable vtable_solo_arm_f64();
+KmVtable vtable_dual_arm_f32();
+KmVtable vtable_dual_arm_f64();
+KmVtable vtable_torso_f32();
+KmVtable vtable_torso_f64();
+}  // namespace km
+
+using km::KmArgs;
+using km::KmVtable;
+
+static thread_local std::string g_err;
+
+struct km_sim {
+  KmVtable vt;
+  int scene, dtype, n, device, act_dim;
+  unsigned long long seed, env0;
+  int G, epb, grid, ctas_per_sm, num_sms;
+  void* d_model;
+  void* d_state;
+  int *d_step, *d_episode, *d_niter, *d_ls;
+  // staging for the host-buffer entry points
+  float* d_act;
+  void *d_obs, *d_reward, *d_xyz;
+  unsigned char *d_trunc, *d_mask;
+  long long launches;
+};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return KM_ERR_CUDA;
+}
+#define KM_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int configure(km_sim* h, int G, int epb) {
+  if (G == 0) G = h->G;
+  if (G != 8 && G != 16 && G != 32) return fail(KM_ERR_ARG, "lanes_per_env must be 8, 16 or 32");
+  int dev_smem = 0;
+  KM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  const size_t model_b = (h->vt.model_bytes + 15) / 16 * 16;
+  if (epb == 0) {
+    // default: the largest CTA that still leaves room for two CTAs per SM (shared memory is the limiter)
+    int sm_total = 0;
+    KM_CUDA(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+    const size_t per_cta = (size_t)sm_total / 2 - 1024;
+    epb = (int)((per_cta - model_b) / h->vt.env_bytes);
+    if (epb * G > 512) epb = 512 / G;
+    if (epb < 1) epb = (int)(((size_t)dev_smem - model_b) / h->vt.env_bytes);
+  }
+  if (epb < 1 || epb * G > 512) return fail(KM_ERR_ARG, "envs_per_block out of range (1 .. 512 / lanes_per_env)");
+  if (model_b + (size_t)epb * h->vt.env_bytes > (size_t)dev_smem)
+    return fail(KM_ERR_ARG, "envs_per_block needs more shared memory than a CTA can opt in to");
+  int ctas = 0;
+  KM_CUDA(h->vt.prepare(G, epb, &ctas));
+  if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
+  h->G = G; h->epb = epb; h->ctas_per_sm = ctas;
+  const long tiles = ((long)h->n + epb - 1) / epb;
+  const long resident = (long)h->num_sms * ctas;
+  h->grid = (int)(tiles < resident ? tiles : resident);
+  return KM_OK;
+}
+
+static KmArgs base_args(km_sim* h, void* stream) {
+  KmArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.model = h->d_model; a.state = h->d_state; a.step = h->d_step; a.episode = h->d_episode;
+  a.niter = h->d_niter; a.ls = h->d_ls;
+  a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid;
+  a.stream = (cudaStream_t)stream;
+  return a;
+}
+
+extern "C" {
+
+const char* km_last_error(void) { return g_err.c_str(); }
+const char* km_version(void) { return "kmanip_b200 0.1 (sm_100a)"; }
+
+int km_create(const km_model* model, const km_task* task, int scene, int n_envs, int device, int dtype,
+              uint64_t seed, uint64_t env0, km_handle* out) {
+  if (!model || !task || !out || n_envs < 1) return fail(KM_ERR_ARG, "km_create: bad argument");
+  if (dtype != KM_F32 && dtype != KM_F64) return fail(KM_ERR_ARG, "km_create: dtype must be 32 or 64");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(KM_ERR_NODEVICE, "km_create: no usable CUDA device (this library has no CPU path)");
+  }
+  km_sim* h = new km_sim();
+  std::memset((void*)h, 0, sizeof(*h));
+  switch (scene * 2 + (dtype == KM_F64)) {
+    case 0: h->vt = km::vtable_solo_arm_f32(); break;
+    case 1: h->vt = km::vtable_solo_arm_f64(); break;
+    case 2: h->vt = km::vtable_dual_arm_f32(); break;
+    case 3: h->vt = km::vtable_dual_arm_f64(); break;
+    case 4: h->vt = km::vtable_torso_f32(); break;
+    case 5: h->vt = km::vtable_torso_f64(); break;
+    default: delete h; return fail(KM_ERR_ARG, "km_create: unknown scene");
+  }
+  h->scene = scene; h->dtype = dtype; h->n = n_envs; h->device = device; h->seed = seed; h->env0 = env0; h->act_dim = task->act_dim;
+  std::vector<unsigned char> host_model(h->vt.model_bytes);
+  std::string err;
+  if (h->vt.fill(model, task, host_model.data(), err) != 0) { delete h; return fail(KM_ERR_MODEL, err); }
+  DeviceGuard guard(device);
+  if (!guard.ok) { delete h; return fail(KM_ERR_CUDA, "km_create: cudaSetDevice failed"); }
+  cudaError_t e;
+  const size_t sb = h->vt.scalar_bytes, n = (size_t)n_envs;
+#define KM_ALLOC(ptr, bytes) if ((e = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) { km_destroy(h); return cuda_fail(e, "cudaMalloc"); }
+  KM_ALLOC(h->d_model, h->vt.model_bytes);
+  KM_ALLOC(h->d_state, n * h->vt.state_dim * sb);
+  KM_ALLOC(h->d_step, n * sizeof(int));
+  KM_ALLOC(h->d_episode, n * sizeof(int));
+  KM_ALLOC(h->d_niter, n * sizeof(int));
+  KM_ALLOC(h->d_ls, n * sizeof(int));
+  KM_ALLOC(h->d_act, n * task->act_dim * sizeof(float));
+  KM_ALLOC(h->d_obs, n * h->vt.obs_dim * sb);
+  KM_ALLOC(h->d_reward, n * sb);
+  KM_ALLOC(h->d_xyz, n * 3 * sb);
+  KM_ALLOC(h->d_trunc, n);
+  KM_ALLOC(h->d_mask, n);
+#undef KM_ALLOC
+  if ((e = cudaMemcpy(h->d_model, host_model.data(), h->vt.model_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemset(h->d_state, 0, n * h->vt.state_dim * sb)) != cudaSuccess ||
+      (e = cudaMemset(h->d_step, 0, n * sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(h->d_episode, 0xff, n * sizeof(int))) != cudaSuccess ||   // -1: the first reset starts episode 0
+      (e = cudaMemset(h->d_niter, 0, n * sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(h->d_ls, 0, n * sizeof(int))) != cudaSuccess) {
+    km_destroy(h);
+    return cuda_fail(e, "km_create: initialisation");
+  }
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  h->G = h->vt.nv <= 16 ? 16 : 32;
+  int rc = configure(h, h->G, 0);
+  if (rc != KM_OK) { km_destroy(h); return rc; }
+  *out = h;
+  return KM_OK;
+}
+
+void km_destroy(km_handle h) {
+  if (!h) return;
+  DeviceGuard guard(h->device);
+  void* ptrs[] = {h->d_model, h->d_state, h->d_step, h->d_episode, h->d_niter, h->d_ls, h->d_act, h->d_obs, h->d_reward,
+                  h->d_xyz, h->d_trunc, h->d_mask};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+}
+
+int km_nq(km_handle h) { return h->vt.nq; }
+int km_nv(km_handle h) { return h->vt.nv; }
+int km_nu(km_handle h) { return h->vt.nu; }
+int km_nmocap(km_handle h) { return h->vt.nmocap; }
+int km_obs_dim(km_handle h) { return h->vt.obs_dim; }
+int km_act_dim(km_handle h) { return h->act_dim; }
+int km_state_dim(km_handle h) { return h->vt.state_dim; }
+int km_max_contacts(km_handle h) { return h->vt.maxcon; }
+int km_num_envs(km_handle h) { return h->n; }
+int km_dtype(km_handle h) { return h->dtype; }
+long long km_launch_count(km_handle h) { return h->launches; }
+void* km_state_ptr(km_handle h) { return h->d_state; }
+
+int km_configure(km_handle h, int lanes_per_env, int envs_per_block) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  return configure(h, lanes_per_env, envs_per_block);
+}
+
+int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* grid, int* ctas_per_sm, int* smem_bytes) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  if (lanes_per_env) *lanes_per_env = h->G;
+  if (envs_per_block) *envs_per_block = h->epb;
+  if (grid) *grid = h->grid;
+  if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
+  if (smem_bytes) *smem_bytes = (int)((h->vt.model_bytes + 15) / 16 * 16 + (size_t)h->epb * h->vt.env_bytes);
+  return KM_OK;
+}
+
+int km_reset(km_handle h, const unsigned char* mask_dev, const void* cube_xyz_dev, void* obs_dev, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  KmArgs a = base_args(h, stream);
+  a.mask = mask_dev; a.cube_xyz = cube_xyz_dev; a.obs = obs_dev;
+  KM_CUDA(h->vt.reset(a));
+  h->launches++;
+  return KM_OK;
+}
+
+int km_step(km_handle h, const float* action_dev, const km_step_out* out, int autoreset, void* stream) {
+  if (!h || !action_dev) return fail(KM_ERR_ARG, "km_step: null handle or action");
+  DeviceGuard guard(h->device);
+  KmArgs a = base_args(h, stream);
+  a.act = action_dev; a.autoreset = autoreset;
+  if (out) {
+    a.obs = out->obs; a.final_obs = out->final_obs; a.reward = out->reward; a.trunc = out->truncated; a.term = out->terminated;
+    a.con_flags = out->con_flags; a.ncon = out->ncon; a.con_geoms = out->con_geoms;
+  }
+  KM_CUDA(h->vt.step(a));
+  h->launches++;
+  return KM_OK;
+}
+
+int km_get_state(km_handle h, void* state_dev, int* step_count_dev, int* episode_dev, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n;
+  if (state_dev) KM_CUDA(cudaMemcpyAsync(state_dev, h->d_state, n * h->vt.state_dim * h->vt.scalar_bytes, cudaMemcpyDeviceToDevice, s));
+  if (step_count_dev) KM_CUDA(cudaMemcpyAsync(step_count_dev, h->d_step, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (episode_dev) KM_CUDA(cudaMemcpyAsync(episode_dev, h->d_episode, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return KM_OK;
+}
+
+int km_set_state(km_handle h, const void* state_dev, const int* step_count_dev, const int* episode_dev, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n;
+  if (state_dev) KM_CUDA(cudaMemcpyAsync(h->d_state, state_dev, n * h->vt.state_dim * h->vt.scalar_bytes, cudaMemcpyDeviceToDevice, s));
+  if (step_count_dev) KM_CUDA(cudaMemcpyAsync(h->d_step, step_count_dev, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (episode_dev) KM_CUDA(cudaMemcpyAsync(h->d_episode, episode_dev, n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return KM_OK;
+}
+
+int km_contacts(km_handle h, int* ncon_dev, int* con_geoms_dev, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  KmArgs a = base_args(h, stream);
+  a.ncon = ncon_dev; a.con_geoms = con_geoms_dev;
+  KM_CUDA(h->vt.contacts(a));
+  h->launches++;
+  return KM_OK;
+}
+
+int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (niter_dev) KM_CUDA(cudaMemcpyAsync(niter_dev, h->d_niter, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (ls_evals_dev) KM_CUDA(cudaMemcpyAsync(ls_evals_dev, h->d_ls, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return KM_OK;
+}
+
+int km_reset_host(km_handle h, const unsigned char* mask, const void* cube_xyz, void* obs) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  const size_t n = (size_t)h->n, sb = h->vt.scalar_bytes;
+  if (mask) KM_CUDA(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, 0));
+  if (cube_xyz) KM_CUDA(cudaMemcpyAsync(h->d_xyz, cube_xyz, n * 3 * sb, cudaMemcpyHostToDevice, 0));
+  int rc = km_reset(h, mask ? h->d_mask : nullptr, cube_xyz ? h->d_xyz : nullptr, obs ? h->d_obs : nullptr, nullptr);
+  if (rc != KM_OK) return rc;
+  if (obs) KM_CUDA(cudaMemcpyAsync(obs, h->d_obs, n * h->vt.obs_dim * sb, cudaMemcpyDeviceToHost, 0));
+  KM_CUDA(cudaStreamSynchronize(0));
+  return KM_OK;
+}
+
+int km_step_host(km_handle h, const float* action, void* obs, void* reward, unsigned char* truncated, int autoreset) {
+  if (!h || !action) return fail(KM_ERR_ARG, "km_step_host: null handle or action");
+  DeviceGuard guard(h->device);
+  const size_t n = (size_t)h->n, sb = h->vt.scalar_bytes;
+  int act_dim = km_act_dim(h);
+  KM_CUDA(cudaMemcpyAsync(h->d_act, action, n * act_dim * sizeof(float), cudaMemcpyHostToDevice, 0));
+  km_step_out o;
+  std::memset(&o, 0, sizeof(o));
+  o.obs = obs ? h->d_obs : nullptr; o.reward = reward ? h->d_reward : nullptr; o.truncated = truncated ? h->d_trunc : nullptr;
+  int rc = km_step(h, h->d_act, &o, autoreset, nullptr);
+  if (rc != KM_OK) return rc;
+  if (obs) KM_CUDA(cudaMemcpyAsync(obs, h->d_obs, n * h->vt.obs_dim * sb, cudaMemcpyDeviceToHost, 0));
+  if (reward) KM_CUDA(cudaMemcpyAsync(reward, h->d_reward, n * sb, cudaMemcpyDeviceToHost, 0));
+  if (truncated) KM_CUDA(cudaMemcpyAsync(truncated, h->d_trunc, n, cudaMemcpyDeviceToHost, 0));
+  KM_CUDA(cudaStreamSynchronize(0));
+  return KM_OK;
+}
+
+}  // extern "C"

@@ -1,19 +1,24 @@
-// km_common.cuh -- scalar helpers, compile-time loops and the run-time parameter block.
+// km_common.cuh -- scalar traits, small vector/quaternion algebra and the lane-group primitives.
 //
-// Everything here is usable from device code (nvcc, sm_100a) and from a host compiler (g++), the latter
-// only for tests/hostsim (a CPU emulation of one CUDA thread used to debug the kernel body without a GPU;
-// it is not part of the product path).
+// Execution model of the whole simulator: one *group* of G lanes (G = 8/16/32, all inside one warp)
+// owns one environment whose working set lives in shared memory.  Code is written as bulk-synchronous
+// phases: `KM_FOR(i, n)` distributes n independent items over the lanes, `g.sync()` separates phases,
+// `g.sum()` is a butterfly reduction that leaves the bit-identical result in every lane, so scalar
+// control flow (Newton iterations, line search) stays uniform inside a group.
+//
+// Everything here also compiles with a host compiler (g++) with G = 1; tests/hostsim uses that to run the
+// identical kernel body on the CPU against the oracle while no GPU is attached.  That host build is a
+// debugging aid for tests only, never a product path.
 #pragma once
 #include <cmath>
 #include <cstdint>
-#include <type_traits>
 
 #if defined(__CUDACC__)
 #define KM_HD __host__ __device__ __forceinline__
-#define KM_HDN __host__ __device__ __noinline__
+#define KM_FN __host__ __device__
 #else
 #define KM_HD inline
-#define KM_HDN inline
+#define KM_FN
 #endif
 
 namespace km {
@@ -34,8 +39,9 @@ template <> struct Num<float> {
     *s = sinf(x); *c = cosf(x);
 #endif
   }
-  static constexpr float eps = 1.1920929e-7f;
-  static constexpr float minval = 1e-15f;
+  static KM_HD float eps() { return 1.1920929e-7f; }
+  static KM_HD float minval() { return 1e-15f; }
+  static KM_HD float huge() { return 3.0e38f; }
 };
 template <> struct Num<double> {
   static KM_HD double sqrt(double x) { return ::sqrt(x); }
@@ -51,90 +57,178 @@ template <> struct Num<double> {
     *s = ::sin(x); *c = ::cos(x);
 #endif
   }
-  static constexpr double eps = 2.220446049250313e-16;
-  static constexpr double minval = 1e-15;
+  static KM_HD double eps() { return 2.220446049250313e-16; }
+  static KM_HD double minval() { return 1e-15; }
+  static KM_HD double huge() { return 1.0e300; }
 };
 template <typename T> KM_HD T tmax(T a, T b) { return a > b ? a : b; }
 template <typename T> KM_HD T tmin(T a, T b) { return a < b ? a : b; }
 template <typename T> KM_HD T tclip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-// ---------------------------------------------------------------------------------------- compile-time loops
-template <int I> using IC = std::integral_constant<int, I>;
-template <int I, int N, class F> KM_HD void sfor(F&& f) {
-  if constexpr (I < N) { f(IC<I>{}); sfor<I + 1, N>(static_cast<F&&>(f)); }
+// ---------------------------------------------------------------------------------------- lane group
+template <int G> struct Grp {
+  int lane;        // 0..G-1 inside the group
+  unsigned mask;   // the group's lanes inside its warp
+  KM_HD void sync() const {
+#if defined(__CUDA_ARCH__)
+    __syncwarp(mask);
+#endif
+  }
+  template <typename T> KM_HD T sum(T v) const {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+#endif
+    return v;
+  }
+  KM_HD bool any(bool p) const {
+#if defined(__CUDA_ARCH__)
+    return (__ballot_sync(mask, p) & mask) != 0u;
+#else
+    return p;
+#endif
+  }
+};
+#define KM_FOR(i, n) for (int i = g.lane; i < (n); i += G)
+
+// ---------------------------------------------------------------------------------------- 3-vectors, quaternions (wxyz)
+template <typename T> KM_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T> KM_HD void cross3(T* r, const T* a, const T* b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
 }
-// I = N-1 ... 0
-template <int N, class F> KM_HD void sfor_rev(F&& f) {
-  if constexpr (N > 0) { f(IC<N - 1>{}); sfor_rev<N - 1>(static_cast<F&&>(f)); }
+// normalise in place, return the norm; degenerate vectors become (1,0,0) (mju_normalize3)
+template <typename T> KM_HD T normalize3(T* a) {
+  T n = Num<T>::sqrt(dot3(a, a));
+  if (n < Num<T>::minval()) { a[0] = 1; a[1] = 0; a[2] = 0; }
+  else { T s = T(1) / n; a[0] *= s; a[1] *= s; a[2] *= s; }
+  return n;
+}
+template <typename T> KM_HD void qnormalize(T* q) {
+  T n = Num<T>::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < Num<T>::minval()) { q[0] = 1; q[1] = 0; q[2] = 0; q[3] = 0; }
+  else { T s = T(1) / n; q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+}
+template <typename T> KM_HD void qmul(T* r, const T* a, const T* b) {
+  T t0 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  T t1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  T t2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  T t3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+// rotation matrix (row-major) of a unit quaternion (mju_quat2Mat)
+template <typename T> KM_HD void q2mat(T* m, const T* q) {
+  T q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  T q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = T(2) * (q12 - q03); m[2] = T(2) * (q13 + q02);
+  m[3] = T(2) * (q12 + q03); m[5] = T(2) * (q23 - q01);
+  m[6] = T(2) * (q13 - q02); m[7] = T(2) * (q23 + q01);
+}
+template <typename T> KM_HD void mulv3(T* r, const T* m, const T* v) {
+  T x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+    z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> KM_HD void mulTv3(T* r, const T* m, const T* v) {
+  T x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2],
+    z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+// mju_mat2Quat
+template <typename T> KM_HD void mat2quat(T* q, const T* m) {
+  typedef Num<T> N;
+  if (m[0] + m[4] + m[8] > T(0)) {
+    q[0] = T(0.5) * N::sqrt(T(1) + m[0] + m[4] + m[8]);
+    q[1] = T(0.25) * (m[7] - m[5]) / q[0]; q[2] = T(0.25) * (m[2] - m[6]) / q[0]; q[3] = T(0.25) * (m[3] - m[1]) / q[0];
+  } else if (m[0] > m[4] && m[0] > m[8]) {
+    q[1] = T(0.5) * N::sqrt(T(1) + m[0] - m[4] - m[8]);
+    q[0] = T(0.25) * (m[7] - m[5]) / q[1]; q[2] = T(0.25) * (m[1] + m[3]) / q[1]; q[3] = T(0.25) * (m[2] + m[6]) / q[1];
+  } else if (m[4] > m[8]) {
+    q[2] = T(0.5) * N::sqrt(T(1) - m[0] + m[4] - m[8]);
+    q[0] = T(0.25) * (m[2] - m[6]) / q[2]; q[1] = T(0.25) * (m[1] + m[3]) / q[2]; q[3] = T(0.25) * (m[5] + m[7]) / q[2];
+  } else {
+    q[3] = T(0.5) * N::sqrt(T(1) - m[0] - m[4] + m[8]);
+    q[0] = T(0.25) * (m[3] - m[1]) / q[3]; q[1] = T(0.25) * (m[2] + m[6]) / q[3]; q[2] = T(0.25) * (m[5] + m[7]) / q[3];
+  }
+  qnormalize(q);
+}
+// mju_subQuat: rotation vector taking qb to qa, in qb's frame
+template <typename T> KM_HD void subquat(T* res, const T* qa, const T* qb) {
+  T qneg[4] = {qb[0], -qb[1], -qb[2], -qb[3]}, qd[4];
+  qmul(qd, qneg, qa);
+  T axis[3] = {qd[1], qd[2], qd[3]};
+  T s = normalize3(axis);
+  T speed = T(2) * Num<T>::atan2(s, qd[0]);
+  if (speed > T(3.14159265358979323846)) speed -= T(2.0 * 3.14159265358979323846);
+  res[0] = axis[0] * speed; res[1] = axis[1] * speed; res[2] = axis[2] * speed;
+}
+// mju_makeFrame: complete an orthonormal frame whose first row (the contact normal) is given, second row zero
+template <typename T> KM_HD void makeframe(T* f) {
+  normalize3(f);
+  T* y = f + 3;
+  y[0] = 0; y[1] = 0; y[2] = 0;
+  if (f[1] < T(0.5) && f[1] > T(-0.5)) y[1] = 1; else y[2] = 1;
+  T t = dot3(f, y);
+  y[0] -= t * f[0]; y[1] -= t * f[1]; y[2] -= t * f[2];
+  normalize3(y);
+  cross3(f + 6, f, y);
+}
+// spatial inertia about a point: 10-vector [Ixx Iyy Izz Ixy Ixz Iyz, m*off(3), m]; 6-vectors are [angular; linear]
+template <typename T> KM_HD void inert_com(T* res, const T* inert, const T* mat, const T* dif, T mass) {
+  T tmp[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      tmp[3 * i + j] = mat[3 * i] * inert[0] * mat[3 * j] + mat[3 * i + 1] * inert[1] * mat[3 * j + 1] +
+                       mat[3 * i + 2] * inert[2] * mat[3 * j + 2];
+  res[0] = tmp[0] + mass * (dif[1] * dif[1] + dif[2] * dif[2]);
+  res[1] = tmp[4] + mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+  res[2] = tmp[8] + mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+  res[3] = tmp[1] - mass * dif[0] * dif[1];
+  res[4] = tmp[2] - mass * dif[0] * dif[2];
+  res[5] = tmp[5] - mass * dif[1] * dif[2];
+  res[6] = mass * dif[0]; res[7] = mass * dif[1]; res[8] = mass * dif[2]; res[9] = mass;
+}
+template <typename T> KM_HD void mul_inert_vec(T* r, const T* i, const T* v) {
+  T a0 = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  T a1 = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  T a2 = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  T a3 = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  T a4 = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  T a5 = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+  r[0] = a0; r[1] = a1; r[2] = a2; r[3] = a3; r[4] = a4; r[5] = a5;
+}
+template <typename T> KM_HD void cross_motion(T* r, const T* vel, const T* v) {
+  T a[3], b[3], c[3];
+  cross3(a, vel, v);
+  cross3(b, vel, v + 3);
+  cross3(c, vel + 3, v);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2];
+  r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+template <typename T> KM_HD void cross_force(T* r, const T* vel, const T* f) {
+  T a[3], b[3], c[3];
+  cross3(a, vel, f);
+  cross3(b, vel + 3, f + 3);
+  cross3(c, vel, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2];
+  r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
 }
 
-// Topology queries evaluated at compile time.
-template <class S> struct Topo {
-  // dof j is i or an ancestor of i in the dof tree
-  static constexpr bool is_anc(int j, int i) {
-    while (i >= 0) { if (i == j) return true; i = S::dof_parent[i]; }
-    return false;
+// Philox4x32-10: the cube-spawn generator, keyed by (seed, global env id, episode) so that results do not
+// depend on how envs are sharded across GPUs.
+KM_HD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  // dof j moves body b
-  static constexpr bool moves(int j, int b) { return S::body_lastdof[b] >= 0 && is_anc(j, S::body_lastdof[b]); }
-  // articulated (non-cube) moving body
-  static constexpr bool arm_body(int b) { return S::body_moving[b] && b != S::CUBE_BODY; }
-  static constexpr bool subtree_has_mass(int b) {
-    for (int c = b; c < S::NBODY; c++) {
-      int a = c; bool in = false;
-      while (a > 0) { if (a == b) { in = true; break; } a = S::body_parent[a]; }
-      if (in && S::body_hasmass[c]) return true;
-    }
-    return false;
-  }
-  // a static body whose world pose some moving child needs
-  static constexpr bool static_parent_needed(int b) {
-    if (S::body_moving[b]) return false;
-    for (int c = 1; c < S::NBODY; c++) if (S::body_parent[c] == b && S::body_moving[c] && c != S::CUBE_BODY) return true;
-    return false;
-  }
-  static constexpr bool has_dof(int b) { return S::body_jtype[b] >= 0; }
-  static constexpr bool fric_on(int d) {
-    for (int k = 0; k < S::NFRIC; k++) if (S::fric_dof[k] == d) return true;
-    return false;
-  }
-  static constexpr int fric_slot(int d) {
-    for (int k = 0; k < S::NFRIC; k++) if (S::fric_dof[k] == d) return k;
-    return -1;
-  }
-  // pad p's Jacobian touches articulated dof d
-  static constexpr bool pad_dof(int p, int d) { return moves(d, S::pad_body[p]); }
-  // dofs d and e can be coupled in the constraint Hessian (same chain ancestry, or linked through a pad to the cube)
-  static constexpr int NCS = S::NPAD + 4;   // contact slots: one per pad, four for the table
-};
-
-// ---------------------------------------------------------------------------------------- run-time parameters
-// Numeric model + task parameters of one scene, passed BY VALUE as the kernel argument (constant bank).
-// Filled on the host by km_api (from the flat km_model) -- see fill_params() there.
-template <class S, typename T> struct Params {
-  // bodies: local frame in the parent for moving bodies, WORLD frame for static bodies
-  T bpos[S::NBODY][3], brot[S::NBODY][9];
-  T bmass[S::NBODY], bipos[S::NBODY][3], binertia[S::NBODY][3];
-  // articulated joints (index == dof == qpos address)
-  T jrange[S::NVA][2], lim_invw[S::NVA], lim_solref[S::NVA][2], lim_solimp[S::NVA][5];
-  // position actuators
-  T kp[S::NU], ctrl_lo[S::NU], ctrl_hi[S::NU], frc_lo[S::NU], frc_hi[S::NU];
-  // friction-loss rows (constant: pos = 0): loss, R, D, B
-  T fr_loss[S::NFRIC > 0 ? S::NFRIC : 1], fr_R[S::NFRIC > 0 ? S::NFRIC : 1], fr_D[S::NFRIC > 0 ? S::NFRIC : 1],
-      fr_B[S::NFRIC > 0 ? S::NFRIC : 1];
-  // finger pads (spheres) and their contact pairs with the cube
-  T pad_pos[S::NPAD][3], pad_rad[S::NPAD];
-  T pad_solref[S::NPAD][2], pad_solimp[S::NPAD][5], pad_mu[S::NPAD][3], pad_tran[S::NPAD], pad_rot[S::NPAD];
-  // table plane z = tab_z and its pair with the cube
-  T tab_z, tab_solref[2], tab_solimp[5], tab_mu[3], tab_tran, tab_rot;
-  T cube_size[3];
-  // options
-  T h, grav[3], tol, ls_tol, meaninertia, impratio;
-  int iterations, ls_iterations;
-  // task
-  T q_home[S::Q_LEN], spawn_lo[3], spawn_hi[3], cube_quat0[4], mocap0[S::NMOCAP * 7];
-  int act_dim, off_pos[2], off_orn[2], off_grip[2], off_q[2], n_arm_act;
-  int ik_iters, ik_teleport, max_episode_steps;
-};
+}
+KM_HD void spawn_uniforms(uint64_t seed, uint64_t env_id, uint32_t episode, double u[3]) {
+  uint32_t c[4] = {(uint32_t)env_id, (uint32_t)(env_id >> 32), episode, 0x4b4d414eu};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int i = 0; i < 3; i++) u[i] = (double)(c[i] >> 8) * (1.0 / 16777216.0);
+}
 
 }  // namespace km

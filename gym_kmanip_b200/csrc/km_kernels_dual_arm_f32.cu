@@ -1,0 +1,3 @@
+// Kernels of the dual_arm scene in float precision (one translation unit per instantiation so they compile in parallel).
+#include "km_launch.cuh"
+namespace km { KmVtable vtable_dual_arm_f32() { return Launch<SceneDualArm, float>::vtable(); } }

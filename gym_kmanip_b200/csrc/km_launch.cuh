@@ -1,0 +1,205 @@
+// km_launch.cuh -- the CUDA kernels around km_sim.cuh and their launchers, instantiated once per
+// (scene, scalar type) translation unit (km_kernels_*.cu) and reached from km_api.cu through KmVtable.
+//
+// Mapping: a CTA holds `epb` environments, each owned by a group of G lanes of one warp; the working set of
+// every env (Env<S,T>) and one copy of the model tables live in dynamic shared memory; the grid is persistent
+// (a multiple of the SM count) and strides over env tiles.  HBM sees one contiguous state record per env in,
+// one out, plus the action / observation / reward records -- everything else stays on chip for all 10 sub-steps.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "km_fill.h"
+
+namespace km {
+
+struct KmArgs {
+  const void* model;
+  void* state;
+  int* step;
+  int* episode;
+  const float* act;
+  void* obs;
+  void* final_obs;
+  void* reward;
+  unsigned char* trunc;
+  unsigned char* term;
+  int* con_flags;
+  int* ncon;
+  int* con_geoms;
+  int* niter;
+  int* ls;
+  const unsigned char* mask;
+  const void* cube_xyz;
+  int n, autoreset;
+  unsigned long long seed, env0;
+  int G, epb, grid;
+  cudaStream_t stream;
+};
+
+struct KmVtable {
+  size_t model_bytes, env_bytes, scalar_bytes;
+  int nq, nv, nu, nmocap, obs_dim, state_dim, maxcon, nlanes_min;
+  int (*fill)(const km_model*, const km_task*, void* dst, std::string& err);
+  cudaError_t (*step)(const KmArgs&);
+  cudaError_t (*reset)(const KmArgs&);
+  cudaError_t (*contacts)(const KmArgs&);
+  // opt in to the dynamic shared memory of (G, epb); returns resident CTAs per SM through *ctas_per_sm
+  cudaError_t (*prepare)(int G, int epb, int* ctas_per_sm);
+};
+
+#if defined(__CUDACC__)
+
+template <class S, typename T> constexpr size_t model_smem() { return (sizeof(Model<S, T>) + 15) / 16 * 16; }
+template <class S, typename T> constexpr size_t env_smem() { return (sizeof(Env<S, T>) + 15) / 16 * 16; }
+template <class S, typename T> size_t smem_bytes(int epb) { return model_smem<S, T>() + (size_t)epb * env_smem<S, T>(); }
+
+template <int G> __device__ __forceinline__ Grp<G> make_group() {
+  Grp<G> g;
+  g.lane = threadIdx.x % G;
+  g.mask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (((threadIdx.x & 31) / G) * G));
+  return g;
+}
+
+template <class S, typename T> __device__ __forceinline__ const Model<S, T>& stage_model(unsigned char* smem, const void* gm) {
+  const uint32_t* src = (const uint32_t*)gm;
+  uint32_t* dst = (uint32_t*)smem;
+  for (int i = threadIdx.x; i < (int)(sizeof(Model<S, T>) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return *(const Model<S, T>*)smem;
+}
+
+// state record <-> the leading members of Env (qpos, qvel, ctrl, warm, mocap, time are laid out contiguously)
+template <class S, typename T, int G> __device__ __forceinline__ void load_state(Env<S, T>& e, const KmArgs& a, long env, const Grp<G>& g) {
+  constexpr int SD = Dim<S>::NQ + 2 * Dim<S>::NV + Dim<S>::NU + 7 * Dim<S>::NMOCAP + 1;
+  typedef Env<S, T> E_;
+  static_assert(offsetof(E_, time) == (SD - 1) * sizeof(T), "state members of Env must be contiguous");
+  const T* src = (const T*)a.state + env * SD;
+  T* dst = (T*)&e;
+  KM_FOR(i, SD) dst[i] = src[i];
+  if (g.lane == 0) { e.step = a.step[env]; e.episode = a.episode[env]; }
+  g.sync();
+}
+template <class S, typename T, int G> __device__ __forceinline__ void store_state(const Env<S, T>& e, const KmArgs& a, long env, const Grp<G>& g) {
+  constexpr int SD = Dim<S>::NQ + 2 * Dim<S>::NV + Dim<S>::NU + 7 * Dim<S>::NMOCAP + 1;
+  T* dst = (T*)a.state + env * SD;
+  const T* src = (const T*)&e;
+  KM_FOR(i, SD) dst[i] = src[i];
+  if (g.lane == 0) { a.step[env] = e.step; a.episode[env] = e.episode; }
+}
+
+template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_env_step(KmArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Model<S, T>& m = stage_model<S, T>(smem, a.model);
+  const Grp<G> g = make_group<G>();
+  const int slot = threadIdx.x / G;
+  Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
+  init_env<S, T, G>(e, m, g);
+  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON};
+  for (long env = (long)blockIdx.x * a.epb + slot; env < a.n; env += (long)gridDim.x * a.epb) {
+    load_state<S, T, G>(e, a, env, g);
+    env_step<S, T, G>(e, m, g, a.act + env * m.act_dim, o, env, a.autoreset, a.seed, a.env0);
+    store_state<S, T, G>(e, a, env, g);
+    if (g.lane == 0) {
+      if (a.niter) a.niter[env] = e.solver_niter;
+      if (a.ls) a.ls[env] = e.ls_evals;
+    }
+    g.sync();
+  }
+}
+
+template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_reset(KmArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Model<S, T>& m = stage_model<S, T>(smem, a.model);
+  const Grp<G> g = make_group<G>();
+  const int slot = threadIdx.x / G;
+  Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
+  for (long env = (long)blockIdx.x * a.epb + slot; env < a.n; env += (long)gridDim.x * a.epb) {
+    if (a.mask && !a.mask[env]) continue;
+    if (g.lane == 0) { e.episode = a.episode[env] + 1; }
+    g.sync();
+    reset_state<S, T, G>(e, m, g, a.seed, a.env0 + (unsigned long long)env, a.cube_xyz ? (const T*)a.cube_xyz + 3 * env : (const T*)0);
+    observation<S, T, G>(e, m, g);
+    if (a.obs) KM_FOR(i, Dim<S>::OBS) ((T*)a.obs)[env * Dim<S>::OBS + i] = e.obs[i];
+    store_state<S, T, G>(e, a, env, g);
+    g.sync();
+  }
+}
+
+template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_contacts(KmArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Model<S, T>& m = stage_model<S, T>(smem, a.model);
+  const Grp<G> g = make_group<G>();
+  const int slot = threadIdx.x / G;
+  Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
+  constexpr int MC = Dim<S>::MAXCON;
+  for (long env = (long)blockIdx.x * a.epb + slot; env < a.n; env += (long)gridDim.x * a.epb) {
+    load_state<S, T, G>(e, a, env, g);
+    kinematics<S, T, G>(e, m, g);
+    collision<S, T, G>(e, m, g);
+    if (g.lane == 0) {
+      if (a.ncon) a.ncon[env] = e.ncon;
+      if (a.con_geoms)
+        for (int c = 0; c < MC; c++) {
+          int g1 = -1, g2 = -1;
+          if (c < e.ncon) { const int s = e.con_slot[c]; g1 = s < Dim<S>::NPAD ? m.pad_geom[s] : m.table_geom; g2 = m.cube_geom; }
+          a.con_geoms[env * 2 * MC + 2 * c] = g1;
+          a.con_geoms[env * 2 * MC + 2 * c + 1] = g2;
+        }
+    }
+    g.sync();
+  }
+}
+
+template <class S, typename T> struct Launch {
+  typedef Dim<S> D;
+  template <int G> static cudaError_t run(int which, const KmArgs& a) {
+    const size_t sm = smem_bytes<S, T>(a.epb);
+    const dim3 block(a.epb * G), grid(a.grid);
+    if (which == 0) k_env_step<S, T, G><<<grid, block, sm, a.stream>>>(a);
+    else if (which == 1) k_reset<S, T, G><<<grid, block, sm, a.stream>>>(a);
+    else k_contacts<S, T, G><<<grid, block, sm, a.stream>>>(a);
+    return cudaGetLastError();
+  }
+  static cudaError_t dispatch(int which, const KmArgs& a) {
+    switch (a.G) {
+      case 8: return run<8>(which, a);
+      case 16: return run<16>(which, a);
+      case 32: return run<32>(which, a);
+    }
+    return cudaErrorInvalidValue;
+  }
+  static cudaError_t step(const KmArgs& a) { return dispatch(0, a); }
+  static cudaError_t reset(const KmArgs& a) { return dispatch(1, a); }
+  static cudaError_t contacts(const KmArgs& a) { return dispatch(2, a); }
+  template <int G> static cudaError_t prep(int epb, int* ctas) {
+    const size_t sm = smem_bytes<S, T>(epb);
+    cudaError_t err;
+    if ((err = cudaFuncSetAttribute(k_env_step<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_reset<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_contacts<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, sm);
+  }
+  static cudaError_t prepare(int G, int epb, int* ctas) {
+    switch (G) {
+      case 8: return prep<8>(epb, ctas);
+      case 16: return prep<16>(epb, ctas);
+      case 32: return prep<32>(epb, ctas);
+    }
+    return cudaErrorInvalidValue;
+  }
+  static int fill(const km_model* fm, const km_task* tk, void* dst, std::string& err) {
+    return fill_model<S, T>(fm, tk, (Model<S, T>*)dst, err);
+  }
+  static KmVtable vtable() {
+    KmVtable v;
+    v.model_bytes = sizeof(Model<S, T>); v.env_bytes = env_smem<S, T>(); v.scalar_bytes = sizeof(T);
+    v.nq = D::NQ; v.nv = D::NV; v.nu = D::NU; v.nmocap = D::NMOCAP; v.obs_dim = D::OBS;
+    v.state_dim = D::NQ + 2 * D::NV + D::NU + 7 * D::NMOCAP + 1; v.maxcon = D::MAXCON; v.nlanes_min = 8;
+    v.fill = &fill; v.step = &step; v.reset = &reset; v.contacts = &contacts; v.prepare = &prepare;
+    return v;
+  }
+};
+
+#endif  // __CUDACC__
+
+}  // namespace km

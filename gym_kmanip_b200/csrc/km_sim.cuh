@@ -1,0 +1,1075 @@
+// km_sim.cuh -- the env-step hot path as lane-group cooperative code (see km_common.cuh for the model).
+//
+// What each routine replaces in the reference (gym-kmanip) is cited at the routine; third-party MuJoCo /
+// dm_control semantics follow SURVEY.md Appendix A.  Per env-step (dm_control legacy_step ordering, A1):
+//     load state -> step1 -> before_step (action decode + IK) -> step2 -> 9 x (step1, step2) -> step1(light)
+//     -> reward, observation, truncation / autoreset -> store state
+// where step1 = position + velocity stage, step2 = actuation + smooth acceleration + Newton constraint
+// solve + semi-implicit Euler.
+#pragma once
+#include "km_model.cuh"
+
+namespace km {
+
+#define KM_TPL template <class S, typename T, int G>
+#define KM_ARGS Env<S, T>& e, const Model<S, T>& m, const Grp<G>& g
+
+// =========================================================================================== position stage
+// mj_kinematics for the articulated links (level by level) and the cube.
+KM_TPL KM_FN void kinematics(KM_ARGS) {
+  typedef Dim<S> D;
+  typedef Num<T> N;
+  if (g.lane == G - 1) {   // cube: normalise the quaternion in place as mj_kinematics does
+    qnormalize(e.qpos + D::NVA + 3);
+    q2mat(e.cmat, e.qpos + D::NVA + 3);
+  }
+  for (int lv = 0; lv < m.nlevel; lv++) {
+    for (int k = m.level_adr[lv] + g.lane; k < m.level_adr[lv + 1]; k += G) {
+      const int l = m.level_link[k], p = m.parent[l];
+      T q[4], pos[3], mat[9];
+      if (p < 0) {
+        for (int i = 0; i < 4; i++) q[i] = m.lquat[l][i];
+        for (int i = 0; i < 3; i++) pos[i] = m.lpos[l][i];
+      } else {
+        qmul(q, e.xquat[p], m.lquat[l]);
+        mulv3(pos, e.xmat[p], m.lpos[l]);
+        for (int i = 0; i < 3; i++) pos[i] += e.xpos[p][i];
+      }
+      const T th = e.qpos[l];
+      if (m.jtype[l] == JT_HINGE) {   // rotate about local z: q <- q * (c, 0, 0, s)
+        T s, c;
+        N::sincos(th * T(0.5), &s, &c);
+        T t0 = q[0] * c - q[3] * s, t1 = q[1] * c + q[2] * s, t2 = q[2] * c - q[1] * s, t3 = q[3] * c + q[0] * s;
+        q[0] = t0; q[1] = t1; q[2] = t2; q[3] = t3;
+      }
+      qnormalize(q);
+      q2mat(mat, q);
+      if (m.jtype[l] == JT_SLIDE) { pos[0] += mat[2] * th; pos[1] += mat[5] * th; pos[2] += mat[8] * th; }
+      for (int i = 0; i < 4; i++) e.xquat[l][i] = q[i];
+      for (int i = 0; i < 9; i++) e.xmat[l][i] = mat[i];
+      T ip[3];
+      mulv3(ip, mat, m.ipos[l]);
+      for (int i = 0; i < 3; i++) { e.xpos[l][i] = pos[i]; e.xipos[l][i] = pos[i] + ip[i]; }
+    }
+    g.sync();
+  }
+}
+
+// mj_comPos: robot-tree centre of mass, cinert and cdof about it; mj_crb: mass matrix.
+KM_TPL KM_FN void com_crb(KM_ARGS) {
+  typedef Dim<S> D;
+  KM_FOR(k, 3) {
+    T s = 0;
+    for (int l = 0; l < D::NVA; l++) s += m.mass[l] * e.xipos[l][k];
+    e.com[k] = s * m.total_mass_inv;
+  }
+  g.sync();
+  KM_FOR(l, D::NVA) {
+    T off[3] = {e.xipos[l][0] - e.com[0], e.xipos[l][1] - e.com[1], e.xipos[l][2] - e.com[2]};
+    T ci[10];
+    inert_com(ci, m.inertia[l], e.xmat[l], off, m.mass[l]);
+    for (int i = 0; i < 10; i++) e.cinert[l][i] = ci[i];
+    const T ax[3] = {e.xmat[l][2], e.xmat[l][5], e.xmat[l][8]};
+    if (m.jtype[l] == JT_SLIDE) {
+      e.cdof[l][0] = 0; e.cdof[l][1] = 0; e.cdof[l][2] = 0;
+      e.cdof[l][3] = ax[0]; e.cdof[l][4] = ax[1]; e.cdof[l][5] = ax[2];
+    } else {
+      T o[3] = {e.com[0] - e.xpos[l][0], e.com[1] - e.xpos[l][1], e.com[2] - e.xpos[l][2]}, c[3];
+      cross3(c, ax, o);
+      e.cdof[l][0] = ax[0]; e.cdof[l][1] = ax[1]; e.cdof[l][2] = ax[2];
+      e.cdof[l][3] = c[0]; e.cdof[l][4] = c[1]; e.cdof[l][5] = c[2];
+    }
+  }
+  g.sync();
+  // composite inertia of link i's subtree times its own motion axis, projected on the ancestors' axes
+  KM_FOR(i, D::NVA) {
+    T crb[10];
+    for (int k = 0; k < 10; k++) crb[k] = e.cinert[i][k];
+    for (int c = i + 1; c < m.sub_end[i]; c++)
+      for (int k = 0; k < 10; k++) crb[k] += e.cinert[c][k];
+    T buf[6];
+    mul_inert_vec(buf, crb, e.cdof[i]);
+    for (int j = i; j >= 0; j = m.parent[j]) {
+      T s = 0;
+      for (int k = 0; k < 6; k++) s += e.cdof[j][k] * buf[k];
+      e.M[i][j] = s; e.M[j][i] = s;
+    }
+  }
+  g.sync();
+}
+
+// Dense Cholesky A = L L^T of the leading n x n block, one lane per row, in place (strict lower triangle
+// holds L, diag[] holds the pivots).  A has row stride `ld`.
+KM_TPL KM_FN void chol_factor(T* A, T* diag, int n, int ld, const Grp<G>& g) {
+  for (int j = 0; j < n; j++) {
+    for (int i = j + g.lane; i < n; i += G) {
+      T s = A[i * ld + j];
+      for (int k = 0; k < j; k++) s -= A[i * ld + k] * A[j * ld + k];
+      A[i * ld + j] = s;
+    }
+    g.sync();
+    const T d = Num<T>::sqrt(tmax(A[j * ld + j], Num<T>::minval())), inv = T(1) / d;   // A[j][j] keeps the unscaled pivot
+    for (int i = j + g.lane; i < n; i += G) {
+      if (i == j) diag[j] = d;
+      else A[i * ld + j] *= inv;
+    }
+    g.sync();
+  }
+}
+// x <- A^{-1} x for a factor produced by chol_factor
+KM_TPL KM_FN void chol_solve(const T* A, const T* diag, T* x, int n, int ld, const Grp<G>& g) {
+  for (int j = 0; j < n; j++) {
+    const T y = x[j] / diag[j];
+    g.sync();
+    for (int i = j + g.lane; i < n; i += G) {
+      if (i == j) x[j] = y;
+      else x[i] -= A[i * ld + j] * y;
+    }
+    g.sync();
+  }
+  for (int j = n - 1; j >= 0; j--) {
+    const T y = x[j] / diag[j];
+    g.sync();
+    for (int i = g.lane; i <= j; i += G) {
+      if (i == j) x[j] = y;
+      else x[i] -= A[j * ld + i] * y;
+    }
+    g.sync();
+  }
+}
+
+KM_TPL KM_FN void factor_m(KM_ARGS) {
+  typedef Dim<S> D;
+  KM_FOR(i, D::NVA)
+    for (int j = 0; j <= i; j++) e.Lm[i][j] = e.M[i][j];
+  g.sync();
+  chol_factor<S, T, G>(&e.Lm[0][0], e.Lmd, D::NVA, D::NVA + 1, g);
+}
+
+// mj_collision on the primitive pairs of the completed model: finger-pad spheres vs the cube box, then the
+// table plane vs the cube's corners (at most four, in corner order).  Contacts are compacted in pair order.
+KM_TPL KM_FN void collision(KM_ARGS) {
+  typedef Dim<S> D;
+  typedef Num<T> N;
+  const T* cpos = e.qpos + D::NVA;
+  KM_FOR(s, D::NSLOT) {
+    int on = 0;
+    T dist = 0, pos[3] = {0, 0, 0}, nrm[3] = {0, 0, 1};
+    if (s < D::NPAD) {   // mjc_SphereBox, sphere = geom1
+      const int l = m.pad_link[s];
+      T c1[3], tmp[3], center[3], cl[3], n[3], pb[3];
+      mulv3(c1, e.xmat[l], m.pad_pos[s]);
+      for (int i = 0; i < 3; i++) tmp[i] = c1[i] + e.xpos[l][i] - cpos[i];
+      mulTv3(center, e.cmat, tmp);
+      for (int i = 0; i < 3; i++) { cl[i] = tclip(center[i], -m.cube_size[i], m.cube_size[i]); n[i] = cl[i] - center[i]; }
+      const T d = N::sqrt(dot3(n, n)), radius = m.pad_rad[s];
+      if (!(d - radius > T(0))) {
+        on = 1;
+        if (d <= N::minval()) {   // centre inside the box: push out through the nearest face
+          T closest = T(2) * (m.cube_size[0] + m.cube_size[1] + m.cube_size[2]);
+          int k = 0;
+          for (int i = 0; i < 6; i++) {
+            T face = (i % 2 ? T(1) : T(-1)) * m.cube_size[i / 2];
+            T t = N::abs(face - center[i / 2]);
+            if (t < closest) { closest = t; k = i; }
+          }
+          T fo[3] = {0, 0, 0};
+          fo[k / 2] = k % 2 ? T(1) : T(-1);
+          for (int i = 0; i < 3; i++) { n[i] = -fo[i]; pb[i] = center[i] + fo[i] * (closest - radius) * T(0.5); }
+          dist = -closest - radius;
+        } else {
+          for (int i = 0; i < 3; i++) n[i] /= d;
+          dist = d - radius;
+          for (int i = 0; i < 3; i++) pb[i] = center[i] + n[i] * (radius + T(0.5) * dist);
+        }
+        mulv3(pos, e.cmat, pb);
+        for (int i = 0; i < 3; i++) pos[i] += cpos[i];
+        mulv3(nrm, e.cmat, n);
+      }
+    } else {             // mjc_PlaneBox: corner i of the cube against z = tab_z, normal (0,0,1)
+      const int i = s - D::NPAD;
+      const T pd = cpos[2] - m.tab_z;
+      T vec[3] = {(i & 1 ? T(1) : T(-1)) * m.cube_size[0], (i & 2 ? T(1) : T(-1)) * m.cube_size[1],
+                  (i & 4 ? T(1) : T(-1)) * m.cube_size[2]}, corner[3];
+      mulv3(corner, e.cmat, vec);
+      const T ld = corner[2];
+      if (!(pd + ld > T(0) || ld > T(0))) {
+        on = 1;
+        dist = pd + ld;
+        pos[0] = corner[0] + cpos[0]; pos[1] = corner[1] + cpos[1]; pos[2] = corner[2] + cpos[2] - dist * T(0.5);
+      }
+    }
+    e.sl_on[s] = on;
+    if (on) {
+      e.sl_dist[s] = dist;
+      T f[9] = {nrm[0], nrm[1], nrm[2], 0, 0, 0, 0, 0, 0};
+      makeframe(f);
+      for (int i = 0; i < 3; i++) e.sl_pos[s][i] = pos[i];
+      for (int i = 0; i < 9; i++) e.sl_frame[s][i] = f[i];
+    }
+  }
+  g.sync();
+  if (g.lane == 0) {
+    int n = 0, corners = 0;
+    for (int s = 0; s < D::NSLOT; s++) {
+      if (!e.sl_on[s]) continue;
+      if (s >= D::NPAD && ++corners > 4) break;
+      e.con_slot[n++] = s;
+    }
+    e.ncon = n;
+  }
+  g.sync();
+}
+
+// solimp -> impedance at penetration `pos` (margin 0)  (SURVEY.md A5).  solimp carries two extra entries,
+// 1 - dmin and 1 - dmax rounded from double, so that 1 - imp keeps full relative precision in fp32 when the
+// impedance is close to one (the cube's solimp gives imp up to 0.9999).  *omi receives 1 - imp.
+template <typename T> KM_HD T impedance(const T* solimp, T pos, T* omi) {
+  typedef Num<T> N;
+  const T dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  const T omin = solimp[5], omax = solimp[6];
+  if (dmin == dmax || width <= N::minval()) { *omi = T(0.5) * (omin + omax); return T(0.5) * (dmin + dmax); }
+  T x = pos / width;
+  if (x < T(0)) x = -x;
+  if (x >= T(1)) { *omi = omax; return dmax; }
+  if (x == T(0)) { *omi = omin; return dmin; }
+  T y;
+  if (power == T(1)) y = x;
+  else if (power == T(2)) y = x <= mid ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
+  else if (x <= mid) y = N::pow(x, power) / N::pow(mid, power - T(1));
+  else y = T(1) - N::pow(T(1) - x, power) / N::pow(T(1) - mid, power - T(1));
+  *omi = omin - y * (dmax - dmin);
+  return dmin + y * (dmax - dmin);
+}
+
+// mj_makeConstraint: friction-loss rows (constant, set up once), active joint limits, pyramidal contact rows,
+// and the contact Jacobian base rows.
+KM_TPL KM_FN void make_constraint(KM_ARGS) {
+  typedef Dim<S> D;
+  typedef Num<T> N;
+  const T* cpos = e.qpos + D::NVA;
+  if (g.lane == 0) {
+    int r = D::NFRIC;
+    for (int j = 0; j < D::NVA; j++) {
+      const T q = e.qpos[j];
+      for (int side = 0; side < 2; side++) {
+        const T dist = side == 0 ? q - m.range[j][0] : m.range[j][1] - q;
+        if (dist < T(0)) {
+          T omi;
+          const T imp = impedance(m.lim_solimp[j], dist, &omi);
+          const T R = tmax(N::minval(), omi * m.lim_invw[j] / imp);
+          const T tc = tmax(m.lim_solref[j][0], T(2) * m.h), dr = m.lim_solref[j][1], dmax = m.lim_solimp[j][1];
+          e.efc_desc[r] = efc_pack(EFC_LIMIT, j, 0, side);
+          e.efc_R[r] = R; e.efc_D[r] = T(1) / R; e.efc_floss[r] = 0;
+          e.efc_B[r] = T(2) / (dmax * tc);
+          e.efc_Kip[r] = (T(1) / (dmax * dmax * tc * tc * dr * dr)) * imp * dist;
+          r++;
+        }
+      }
+    }
+    e.nlim = r - D::NFRIC;
+    e.nefc = r + 6 * e.ncon;
+  }
+  g.sync();
+  const int base = D::NFRIC + e.nlim;
+  KM_FOR(c, e.ncon) {
+    const int s = e.con_slot[c];
+    const T *solref, *solimp, *mu3;
+    T tran;
+    if (s < D::NPAD) { solref = m.pad_solref[s]; solimp = m.pad_solimp[s]; mu3 = m.pad_mu[s]; tran = m.pad_tran[s]; }
+    else { solref = m.tab_solref; solimp = m.tab_solimp; mu3 = m.tab_mu; tran = m.tab_tran; }
+    const T dist = e.sl_dist[s];
+    T omi;
+    const T imp = impedance(solimp, dist, &omi);
+    const T diag1 = tran + mu3[0] * mu3[0] * tran;
+    const T R1 = tmax(N::minval(), omi * diag1 / imp);
+    const T mu = mu3[0] / N::sqrt(m.impratio);
+    const T R = T(2) * mu * mu * R1, Dc = T(1) / R;
+    const T tc = tmax(solref[0], T(2) * m.h), dr = solref[1], dmax = solimp[1];
+    const T B = T(2) / (dmax * tc), Kip = (T(1) / (dmax * dmax * tc * tc * dr * dr)) * imp * dist;
+    e.con_D[c] = Dc;
+    for (int k = 0; k < 3; k++) e.con_mu[c][k] = mu3[k];
+    e.con_sup[c] = (s < D::NPAD ? m.ancmask[m.pad_link[s]] : 0u) | (63u << D::NVA);
+    for (int k = 0; k < 6; k++) {
+      const int r = base + 6 * c + k;
+      e.efc_desc[r] = efc_pack(EFC_CONTACT, c, 1 + k / 2, k & 1);
+      e.efc_R[r] = R; e.efc_D[r] = Dc; e.efc_B[r] = B; e.efc_Kip[r] = Kip; e.efc_floss[r] = 0;
+    }
+  }
+  // contact Jacobian base rows, J = J(cube) - J(pad link), one (contact, dof) per work item
+  KM_FOR(w, e.ncon * D::NV) {
+    const int c = w / D::NV, col = w - c * D::NV, s = e.con_slot[c];
+    const T* f = e.sl_frame[s];
+    const T* p = e.sl_pos[s];
+    T jp[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
+    bool on = true;
+    if (col >= D::NVA) {
+      const int k = col - D::NVA;
+      if (k < 3) jp[k] = 1;
+      else {
+        const T a[3] = {e.cmat[k - 3], e.cmat[3 + k - 3], e.cmat[6 + k - 3]};
+        const T o[3] = {p[0] - cpos[0], p[1] - cpos[1], p[2] - cpos[2]};
+        cross3(jp, a, o);
+        jr[0] = a[0]; jr[1] = a[1]; jr[2] = a[2];
+      }
+    } else if (s < D::NPAD && ((m.ancmask[m.pad_link[s]] >> col) & 1u)) {
+      const T a[3] = {e.xmat[col][2], e.xmat[col][5], e.xmat[col][8]};
+      if (m.jtype[col] == JT_SLIDE) { jp[0] = -a[0]; jp[1] = -a[1]; jp[2] = -a[2]; }
+      else {
+        const T o[3] = {p[0] - e.xpos[col][0], p[1] - e.xpos[col][1], p[2] - e.xpos[col][2]};
+        T t[3];
+        cross3(t, a, o);
+        jp[0] = -t[0]; jp[1] = -t[1]; jp[2] = -t[2];
+        jr[0] = -a[0]; jr[1] = -a[1]; jr[2] = -a[2];
+      }
+    } else on = false;
+    if (on) {
+      e.Jc[c][0][col] = dot3(f, jp);
+      e.Jc[c][1][col] = dot3(f + 3, jp);
+      e.Jc[c][2][col] = dot3(f + 6, jp);
+      e.Jc[c][3][col] = dot3(f, jr);
+    }
+  }
+  g.sync();
+}
+
+// out[r] = J_r . x for every constraint row (x is a dof-space vector in shared memory)
+KM_TPL KM_FN void mul_J(KM_ARGS, const T* x, T* out) {
+  typedef Dim<S> D;
+  KM_FOR(w, e.ncon * 4) {
+    const int c = w >> 2, b = w & 3;
+    const unsigned sup = e.con_sup[c];
+    T s = 0;
+    for (int j = 0; j < D::NV; j++)
+      if ((sup >> j) & 1u) s += e.Jc[c][b][j] * x[j];
+    e.cb[c][b] = s;
+  }
+  g.sync();
+  KM_FOR(r, e.nefc) {
+    const int d = e.efc_desc[r], id = efc_id(d);
+    T v;
+    if (efc_type(d) == EFC_CONTACT) {
+      const T t = e.con_mu[id][efc_k(d) - 1] * e.cb[id][efc_k(d)];
+      v = e.cb[id][0] + (efc_neg(d) ? -t : t);
+    } else v = efc_neg(d) ? -x[id] : x[id];
+    out[r] = v;
+  }
+  g.sync();
+}
+
+// e.qfc = J^T efc_force
+KM_TPL KM_FN void mul_JT_force(KM_ARGS) {
+  typedef Dim<S> D;
+  const int base = D::NFRIC + e.nlim;
+  KM_FOR(c, e.ncon) {
+    const T* f = e.efc_force + base + 6 * c;
+    e.cb[c][0] = f[0] + f[1] + f[2] + f[3] + f[4] + f[5];
+    e.cb[c][1] = e.con_mu[c][0] * (f[0] - f[1]);
+    e.cb[c][2] = e.con_mu[c][1] * (f[2] - f[3]);
+    e.cb[c][3] = e.con_mu[c][2] * (f[4] - f[5]);
+  }
+  g.sync();
+  KM_FOR(i, D::NV) {
+    T s = 0;
+    for (int r = 0; r < base; r++) {
+      const int d = e.efc_desc[r];
+      if (efc_id(d) == i) s += efc_neg(d) ? -e.efc_force[r] : e.efc_force[r];
+    }
+    for (int c = 0; c < e.ncon; c++)
+      if ((e.con_sup[c] >> i) & 1u)
+        s += e.Jc[c][0][i] * e.cb[c][0] + e.Jc[c][1][i] * e.cb[c][1] + e.Jc[c][2][i] * e.cb[c][2] + e.Jc[c][3][i] * e.cb[c][3];
+    e.qfc[i] = s;
+  }
+  g.sync();
+}
+
+// out = M x  (articulated block: ancestors and subtree of each dof; cube block: constant diagonal)
+KM_TPL KM_FN void mul_M(KM_ARGS, const T* x, T* out) {
+  typedef Dim<S> D;
+  KM_FOR(i, D::NV) {
+    T s;
+    if (i >= D::NVA) {
+      const int k = i - D::NVA;
+      s = (k < 3 ? m.cube_mass : m.cube_inertia[k - 3]) * x[i];
+    } else {
+      s = 0;
+      for (int j = m.parent[i]; j >= 0; j = m.parent[j]) s += e.M[i][j] * x[j];
+      for (int j = i; j < m.sub_end[i]; j++) s += e.M[i][j] * x[j];
+    }
+    out[i] = s;
+  }
+  g.sync();
+}
+
+KM_TPL KM_FN void fwd_position(KM_ARGS) {
+  typedef Dim<S> D;
+  kinematics<S, T, G>(e, m, g);
+  com_crb<S, T, G>(e, m, g);
+  factor_m<S, T, G>(e, m, g);
+  collision<S, T, G>(e, m, g);
+  make_constraint<S, T, G>(e, m, g);
+  KM_FOR(i, D::NU) e.actlen[i] = e.qpos[i];   // mj_transmission: joint transmissions, gear 1
+  g.sync();
+}
+
+// =========================================================================================== velocity stage
+// mj_comVel + mj_rne(flg_acc = 0) + mj_referenceConstraint.
+KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
+  typedef Dim<S> D;
+  KM_FOR(l, D::NVA) {
+    T v[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = l; j >= 0; j = m.parent[j]) {
+      const T qv = e.qvel[j];
+      for (int k = 0; k < 6; k++) v[k] += e.cdof[j][k] * qv;
+    }
+    for (int k = 0; k < 6; k++) e.cvel[l][k] = v[k];
+  }
+  g.sync();
+  KM_FOR(l, D::NVA) {
+    const int p = m.parent[l];
+    T r[6] = {0, 0, 0, 0, 0, 0};
+    if (p >= 0) cross_motion(r, e.cvel[p], e.cdof[l]);
+    for (int k = 0; k < 6; k++) e.cdof_dot[l][k] = r[k];
+  }
+  g.sync();
+  KM_FOR(l, D::NVA) {
+    T a[6] = {0, 0, 0, -m.grav[0], -m.grav[1], -m.grav[2]};
+    for (int j = l; j >= 0; j = m.parent[j]) {
+      const T qv = e.qvel[j];
+      for (int k = 0; k < 6; k++) a[k] += e.cdof_dot[j][k] * qv;
+    }
+    T f[6], t1[6], t2[6];
+    mul_inert_vec(f, e.cinert[l], a);
+    mul_inert_vec(t1, e.cinert[l], e.cvel[l]);
+    cross_force(t2, e.cvel[l], t1);
+    for (int k = 0; k < 6; k++) e.cfrc[l][k] = f[k] + t2[k];
+  }
+  g.sync();
+  KM_FOR(i, D::NV) {
+    T s = 0;
+    if (i < D::NVA) {
+      T f[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = i; c < m.sub_end[i]; c++)
+        for (int k = 0; k < 6; k++) f[k] += e.cfrc[c][k];
+      for (int k = 0; k < 6; k++) s += e.cdof[i][k] * f[k];
+    } else {
+      // free cube with its COM at the body origin: bias = [-m g ; w x (I w)] (w in the body frame)
+      const int k = i - D::NVA;
+      if (k < 3) s = -m.cube_mass * m.grav[k];
+      else {
+        const T* w = e.qvel + D::NVA + 3;
+        const T Iw[3] = {m.cube_inertia[0] * w[0], m.cube_inertia[1] * w[1], m.cube_inertia[2] * w[2]};
+        T c[3];
+        cross3(c, w, Iw);
+        s = c[k - 3];
+      }
+    }
+    e.bias[i] = s;
+  }
+  // reference acceleration of every row: aref = -B (J qvel) - K imp pos
+  mul_J<S, T, G>(e, m, g, e.qvel, e.efc_jv);
+  KM_FOR(r, e.nefc) e.efc_aref[r] = -e.efc_B[r] * e.efc_jv[r] - e.efc_Kip[r];
+  g.sync();
+}
+
+// =========================================================================================== acceleration stage
+// mj_fwdActuation (<position kp> servos) + mj_fwdAcceleration.
+KM_TPL KM_FN void fwd_actuation_acceleration(KM_ARGS) {
+  typedef Dim<S> D;
+  KM_FOR(i, D::NV) {
+    T f = 0;
+    if (i < D::NVA) {
+      const T c = tclip(e.ctrl[i], m.ctrl_lo[i], m.ctrl_hi[i]);
+      f = tclip(m.kp[i] * c - m.kp[i] * e.actlen[i], m.frc_lo[i], m.frc_hi[i]);
+    }
+    const T s = f - e.bias[i];
+    e.qfrc_smooth[i] = s;
+    e.qacc_smooth[i] = i < D::NVA ? s : s / (i - D::NVA < 3 ? m.cube_mass : m.cube_inertia[i - D::NVA - 3]);
+  }
+  g.sync();
+  chol_solve<S, T, G>(&e.Lm[0][0], e.Lmd, e.qacc_smooth, D::NVA, D::NVA + 1, g);
+}
+
+// ---- Newton solver (mj_solNewton on the primal problem)
+// constraint cost pieces of one row at residual x: returns the cost, sets state and force
+template <typename T> KM_HD T row_cost(int type, T x, T Dr, T R, T floss, int* state, T* force) {
+  if (type == EFC_FRICTION) {
+    const T rf = R * floss;
+    if (x <= -rf) { *state = ST_LINEARNEG; *force = floss; return -floss * (T(0.5) * rf + x); }
+    if (x >= rf) { *state = ST_LINEARPOS; *force = -floss; return -floss * (T(0.5) * rf - x); }
+    *state = ST_QUADRATIC; *force = -Dr * x; return T(0.5) * Dr * x * x;
+  }
+  if (x < T(0)) { *state = ST_QUADRATIC; *force = -Dr * x; return T(0.5) * Dr * x * x; }
+  *state = ST_SATISFIED; *force = 0; return 0;
+}
+
+// total cost (constraint + Gauss) at acceleration `a`; uses efc_jv and Mv as scratch
+KM_TPL KM_FN T total_cost(KM_ARGS, const T* a) {
+  typedef Dim<S> D;
+  mul_J<S, T, G>(e, m, g, a, e.efc_jv);
+  mul_M<S, T, G>(e, m, g, a, e.Mv);
+  T c = 0;
+  KM_FOR(r, e.nefc) {
+    int st; T f;
+    c += row_cost(efc_type(e.efc_desc[r]), e.efc_jv[r] - e.efc_aref[r], e.efc_D[r], e.efc_R[r], e.efc_floss[r], &st, &f);
+  }
+  T gs = 0;
+  KM_FOR(i, D::NV) gs += (e.Mv[i] - e.qfrc_smooth[i]) * (a[i] - e.qacc_smooth[i]);
+  c = g.sum(c + T(0.5) * gs);
+  g.sync();
+  return c;
+}
+
+// states, forces, cost and gradient at the current jar / Ma / qacc; returns the total cost, *gauss the Gauss term
+KM_TPL KM_FN T sol_update(KM_ARGS, T* gauss) {
+  typedef Dim<S> D;
+  T c = 0;
+  KM_FOR(r, e.nefc) {
+    int st; T f;
+    c += row_cost(efc_type(e.efc_desc[r]), e.efc_jar[r], e.efc_D[r], e.efc_R[r], e.efc_floss[r], &st, &f);
+    e.efc_state[r] = st; e.efc_force[r] = f;
+  }
+  g.sync();
+  mul_JT_force<S, T, G>(e, m, g);
+  T gs = 0;
+  KM_FOR(i, D::NV) {
+    gs += (e.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
+    e.grad[i] = e.Ma[i] - e.qfrc_smooth[i] - e.qfc[i];
+  }
+  c = g.sum(c);
+  gs = T(0.5) * g.sum(gs);
+  g.sync();
+  *gauss = gs;
+  return c + gs;
+}
+
+// H = M + J^T diag(D_active) J, Cholesky, Mgrad = H^{-1} grad
+KM_TPL KM_FN void sol_hessian_dir(KM_ARGS) {
+  typedef Dim<S> D;
+  const int base = D::NFRIC + e.nlim;
+  // per-contact weights of the base rows: W = sum_active D w w^T, w = e0 +- mu_k e_k  (arrow-head 4x4)
+  KM_FOR(c, e.ncon) {
+    const int* st = e.efc_state + base + 6 * c;
+    const T Dc = e.con_D[c];
+    T n = 0;
+    for (int k = 0; k < 3; k++) {
+      const T p = st[2 * k] == ST_QUADRATIC ? T(1) : T(0), q = st[2 * k + 1] == ST_QUADRATIC ? T(1) : T(0);
+      const T mu = e.con_mu[c][k];
+      n += p + q;
+      e.cb[c][1 + k] = Dc * mu * (p - q);        // W[0][k]
+      e.con_W[c][k] = Dc * mu * mu * (p + q);    // W[k][k]
+    }
+    e.cb[c][0] = Dc * n;                                // W[0][0]
+  }
+  g.sync();
+  KM_FOR(w, D::NV * (D::NV + 1) / 2) {
+    // unrank the lower-triangle index: w = i (i + 1) / 2 + j
+    int i = (int)((Num<float>::sqrt(8.0f * (float)w + 1.0f) - 1.0f) * 0.5f);
+    while (i * (i + 1) / 2 > w) i--;
+    while ((i + 1) * (i + 2) / 2 <= w) i++;
+    const int j = w - i * (i + 1) / 2;
+    T h;
+    if (i < D::NVA) h = e.M[i][j];
+    else h = i == j ? (i - D::NVA < 3 ? m.cube_mass : m.cube_inertia[i - D::NVA - 3]) : T(0);
+    if (i == j)
+      for (int r = 0; r < base; r++)
+        if (efc_id(e.efc_desc[r]) == i && e.efc_state[r] == ST_QUADRATIC) h += e.efc_D[r];
+    for (int c = 0; c < e.ncon; c++) {
+      const unsigned sup = e.con_sup[c];
+      if (((sup >> i) & 1u) && ((sup >> j) & 1u)) {
+        const T ni = e.Jc[c][0][i], nj = e.Jc[c][0][j];
+        T acc = e.cb[c][0] * ni * nj;
+        for (int k = 1; k < 4; k++) {
+          const T ki = e.Jc[c][k][i], kj = e.Jc[c][k][j];
+          acc += e.cb[c][k] * (ni * kj + ki * nj) + e.con_W[c][k - 1] * ki * kj;
+        }
+        h += acc;
+      }
+    }
+    e.H[i][j] = h;
+  }
+  KM_FOR(i, D::NV) e.Mgrad[i] = e.grad[i];
+  g.sync();
+  chol_factor<S, T, G>(&e.H[0][0], e.Hd, D::NV, D::HS, g);
+  chol_solve<S, T, G>(&e.H[0][0], e.Hd, e.Mgrad, D::NV, D::HS, g);
+}
+
+// derivatives of the 1-D cost along the search direction at step alpha
+KM_TPL KM_FN void ls_eval(KM_ARGS, T qg1, T qg2, T alpha, T* d1, T* d2) {
+  T q1 = 0, q2 = 0;
+  KM_FOR(r, e.nefc) {
+    const T jv = e.efc_jv[r], jar = e.efc_jar[r], x = jar + alpha * jv, Dr = e.efc_D[r];
+    if (efc_type(e.efc_desc[r]) == EFC_FRICTION) {
+      const T f = e.efc_floss[r], rf = e.efc_R[r] * f;
+      if (x <= -rf) { q1 += -f * jv; continue; }
+      if (x >= rf) { q1 += f * jv; continue; }
+    } else if (x >= T(0)) continue;
+    q1 += Dr * jar * jv;
+    q2 += T(0.5) * Dr * jv * jv;
+  }
+  q1 = g.sum(q1) + qg1;
+  q2 = g.sum(q2) + qg2;
+  *d1 = T(2) * alpha * q2 + q1;
+  *d2 = T(2) * q2;
+  if (g.lane == 0) e.ls_evals++;
+}
+
+KM_TPL KM_FN T sol_linesearch(KM_ARGS, T scale) {
+  typedef Dim<S> D;
+  typedef Num<T> N;
+  T sn = 0;
+  KM_FOR(i, D::NV) sn += e.search[i] * e.search[i];
+  const T snorm = N::sqrt(g.sum(sn));
+  if (snorm < N::minval()) return 0;
+  mul_M<S, T, G>(e, m, g, e.search, e.Mv);
+  mul_J<S, T, G>(e, m, g, e.search, e.efc_jv);
+  T a1 = 0, a2 = 0;
+  KM_FOR(i, D::NV) {
+    a1 += e.search[i] * (e.Ma[i] - e.qfrc_smooth[i]);
+    a2 += T(0.5) * e.search[i] * e.Mv[i];
+  }
+  const T qg1 = g.sum(a1), qg2 = g.sum(a2);
+  T d1, d2;
+  ls_eval<S, T, G>(e, m, g, qg1, qg2, T(0), &d1, &d2);
+  const T gtol = tmax(m.tol * m.ls_tol * snorm / scale, T(64) * N::eps() * N::abs(d1));
+  if (N::abs(d1) < gtol || d1 > T(0)) return 0;
+  T lo = 0, lo_d1 = d1, lo_d2 = d2, hi = 0, hi_d1 = 0, hi_d2 = 0;
+  int bracket = 0, it = 0;
+  for (; it < m.ls_iterations; it++) {   // Newton steps to the right until the slope changes sign
+    const T a = lo - lo_d1 / lo_d2;
+    ls_eval<S, T, G>(e, m, g, qg1, qg2, a, &d1, &d2);
+    if (N::abs(d1) < gtol) return a;
+    if (d1 > T(0)) { hi = a; hi_d1 = d1; hi_d2 = d2; bracket = 1; break; }
+    lo = a; lo_d1 = d1; lo_d2 = d2;
+  }
+  if (!bracket) return lo;
+  for (; it < m.ls_iterations; it++) {   // safeguarded Newton inside the bracket
+    T a = N::abs(lo_d1) < N::abs(hi_d1) ? lo - lo_d1 / lo_d2 : hi - hi_d1 / hi_d2;
+    if (!(a > lo && a < hi)) a = T(0.5) * (lo + hi);
+    if (a == lo || a == hi) break;
+    ls_eval<S, T, G>(e, m, g, qg1, qg2, a, &d1, &d2);
+    if (N::abs(d1) < gtol) return a;
+    if (d1 > T(0)) { hi = a; hi_d1 = d1; hi_d2 = d2; } else { lo = a; lo_d1 = d1; lo_d2 = d2; }
+  }
+  return N::abs(lo_d1) < N::abs(hi_d1) ? lo : hi;
+}
+
+KM_TPL KM_FN void fwd_constraint(KM_ARGS) {
+  typedef Dim<S> D;
+  typedef Num<T> N;
+  if (g.lane == 0) { e.solver_niter = 0; }
+  // warm start: the previous qacc if it is cheaper than the unconstrained acceleration
+  const T cw = total_cost<S, T, G>(e, m, g, e.warm), cs = total_cost<S, T, G>(e, m, g, e.qacc_smooth);
+  KM_FOR(i, D::NV) e.qacc[i] = cw > cs ? e.qacc_smooth[i] : e.warm[i];
+  g.sync();
+  mul_M<S, T, G>(e, m, g, e.qacc, e.Ma);
+  mul_J<S, T, G>(e, m, g, e.qacc, e.efc_jar);
+  KM_FOR(r, e.nefc) e.efc_jar[r] -= e.efc_aref[r];
+  g.sync();
+  const T scale = T(1) / (m.meaninertia * T(D::NV));
+  T gauss;
+  T cost = sol_update<S, T, G>(e, m, g, &gauss);
+  int niter = 0;
+  while (niter < m.iterations) {
+    sol_hessian_dir<S, T, G>(e, m, g);
+    KM_FOR(i, D::NV) e.search[i] = -e.Mgrad[i];
+    g.sync();
+    const T alpha = sol_linesearch<S, T, G>(e, m, g, scale);
+    if (alpha == T(0)) break;
+    KM_FOR(i, D::NV) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
+    KM_FOR(r, e.nefc) e.efc_jar[r] += alpha * e.efc_jv[r];
+    g.sync();
+    const T oldcost = cost;
+    cost = sol_update<S, T, G>(e, m, g, &gauss);
+    T gn = 0;
+    KM_FOR(i, D::NV) gn += e.grad[i] * e.grad[i];
+    gn = g.sum(gn);
+    niter++;
+    if (scale * (oldcost - cost) < m.tol || scale * N::sqrt(gn) < m.tol) break;
+  }
+  KM_FOR(i, D::NV) e.warm[i] = e.qacc[i];
+  if (g.lane == 0) e.solver_niter = niter;
+  g.sync();
+}
+
+// mj_Euler (no joint damping anywhere): semi-implicit, free-joint quaternion integrated on the manifold (A6)
+KM_TPL KM_FN void euler(KM_ARGS) {
+  typedef Dim<S> D;
+  KM_FOR(i, D::NV) {
+    const T v = e.qvel[i] + m.h * e.qacc[i];
+    e.qvel[i] = v;
+    if (i < D::NVA + 3) e.qpos[i] += m.h * v;
+  }
+  g.sync();
+  if (g.lane == 0) {
+    T w[3] = {e.qvel[D::NVA + 3], e.qvel[D::NVA + 4], e.qvel[D::NVA + 5]};
+    T* q = e.qpos + D::NVA + 3;
+    const T angle = m.h * normalize3(w);
+    T qrot[4] = {1, 0, 0, 0}, t[4];
+    if (angle != T(0)) {
+      T s, c;
+      Num<T>::sincos(angle * T(0.5), &s, &c);
+      qrot[0] = c; qrot[1] = w[0] * s; qrot[2] = w[1] * s; qrot[3] = w[2] * s;
+    }
+    qnormalize(q);
+    qmul(t, q, qrot);
+    q[0] = t[0]; q[1] = t[1]; q[2] = t[2]; q[3] = t[3];
+    e.time += m.h;
+  }
+  g.sync();
+}
+
+KM_TPL KM_FN void step1(KM_ARGS) {
+  fwd_position<S, T, G>(e, m, g);
+  fwd_velocity<S, T, G>(e, m, g);
+}
+KM_TPL KM_FN void step2(KM_ARGS) {
+  fwd_actuation_acceleration<S, T, G>(e, m, g);
+  fwd_constraint<S, T, G>(e, m, g);
+  euler<S, T, G>(e, m, g);
+}
+
+// =========================================================================================== task: action decode + IK
+// site pose of arm a from the current link frames
+KM_TPL KM_FN void site_pose(const Env<S, T>& e, const Model<S, T>& m, int a, T* pos, T* mat) {
+  const int l = m.arm_site_link[a];
+  T t[3], q[4];
+  mulv3(t, e.xmat[l], m.site_pos[a]);
+  for (int i = 0; i < 3; i++) pos[i] = e.xpos[l][i] + t[i];
+  qmul(q, e.xquat[l], m.site_quat[a]);
+  q2mat(mat, q);
+}
+
+// ik_res (reference ik_mujoco.py:20-53) at the joint values currently in qpos (kinematics must be fresh)
+KM_TPL KM_FN void ik_residual(KM_ARGS, int a, const T* x, T* res) {
+  const int n = m.arm_nmask[a];
+  if (g.lane == 0) {
+    T pos[3], mat[9], cur[4], rq[3];
+    site_pose<S, T, G>(e, m, a, pos, mat);
+    for (int i = 0; i < 3; i++) res[i] = pos[i] - e.ik_goal[a][i];
+    mat2quat(cur, mat);
+    subquat(rq, e.ik_goal[a] + 3, cur);
+    for (int i = 0; i < 3; i++) res[3 + i] = rq[i] * T(0.02);                    // IK_RES_RAD
+  }
+  KM_FOR(i, n) {
+    res[6 + i] = T(6e-3) * (x[i] - e.ik_qprev[i]);                               // IK_RES_REG_PREV
+    res[6 + n + i] = T(2e-6) * (x[i] - m.q_home[m.arm_mask[a][i]]);              // IK_RES_REG_HOME
+  }
+  g.sync();
+}
+
+// pose rows of ik_jac (reference ik_mujoco.py:56-97): [Jp ; rad * d subQuat(goal, cur) / dq], columns = mask.
+// The orientation block is -rad * Jl^{-1}(phi) R_site^T Jr with phi = subQuat(goal, cur)  (DESIGN.md).
+KM_TPL KM_FN void ik_jacobian(KM_ARGS, int a) {
+  typedef Num<T> N;
+  const int n = m.arm_nmask[a];
+  KM_FOR(c, n) {
+    T pos[3], R[9], cur[4], phi[3];
+    site_pose<S, T, G>(e, m, a, pos, R);
+    mat2quat(cur, R);
+    subquat(phi, e.ik_goal[a] + 3, cur);
+    T u[3] = {phi[0], phi[1], phi[2]};
+    const T half = T(0.5) * normalize3(u);
+    const T coef = T(1) - (half < T(6e-8) ? T(1) : half / N::tan(half));
+    const T K[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
+    T Dm[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        T kk = 0;
+        for (int k = 0; k < 3; k++) kk += K[3 * i + k] * K[3 * k + j];
+        Dm[3 * i + j] = (i == j ? T(1) : T(0)) - half * K[3 * i + j] + coef * kk;
+      }
+    const int j = m.arm_mask[a][c];
+    const T ax[3] = {e.xmat[j][2], e.xmat[j][5], e.xmat[j][8]};
+    T jp[3], jr[3] = {0, 0, 0};
+    if (m.jtype[j] == JT_SLIDE) { jp[0] = ax[0]; jp[1] = ax[1]; jp[2] = ax[2]; }
+    else {
+      const T o[3] = {pos[0] - e.xpos[j][0], pos[1] - e.xpos[j][1], pos[2] - e.xpos[j][2]};
+      cross3(jp, ax, o);
+      jr[0] = ax[0]; jr[1] = ax[1]; jr[2] = ax[2];
+    }
+    T jl[3], o3[3];
+    mulTv3(jl, R, jr);
+    mulv3(o3, Dm, jl);
+    for (int i = 0; i < 3; i++) { e.ik_J[i][c] = jp[i]; e.ik_J[3 + i][c] = -T(0.02) * o3[i]; }   // IK_JAC_RAD
+  }
+  g.sync();
+}
+
+// Device IK: projected Levenberg-Marquardt on the reference's stationarity condition J^T r = 0 with J, r
+// exactly as ik_jac / ik_res build them (including their mismatched regulariser weights),
+// a fixed iteration count, the bound handling of scipy's TRF at its KKT point, and the reference's side
+// effect of leaving qpos[mask] at the solution (B-1).  Skipped when x0 is out of bounds (B-4).
+KM_TPL KM_FN void ik_solve(KM_ARGS, int a) {
+  typedef Dim<S> D;
+  const int n = m.arm_nmask[a], nr = 6 + 2 * n;
+  T* A = &e.H[0][0];
+  bool bad = false;
+  KM_FOR(i, n) {
+    const int j = m.arm_mask[a][i];
+    const T x = e.qpos[j];
+    e.ik_x[i] = x; e.ik_qprev[i] = x; e.ik_lo[i] = m.range[j][0]; e.ik_hi[i] = m.range[j][1];
+    bad = bad || x < m.range[j][0] || x > m.range[j][1];
+  }
+  const bool feasible = !g.any(bad);
+  g.sync();
+  if (feasible) {
+    const T lam = T(9e-3 * (6e-3 + 2e-6)), reg = T(9e-3);   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)
+    T mu = 0;
+    ik_residual<S, T, G>(e, m, g, a, e.ik_x, e.ik_r);
+    ik_jacobian<S, T, G>(e, m, g, a);
+    T cs = 0;
+    KM_FOR(k, nr) cs += T(0.5) * e.ik_r[k] * e.ik_r[k];
+    T cost = g.sum(cs);
+    for (int it = 0; it < m.ik_iters; it++) {
+      KM_FOR(i, n) {
+        T gi = 0;
+        for (int k = 0; k < 6; k++) gi += e.ik_J[k][i] * e.ik_r[k];
+        gi += reg * e.ik_r[6 + i] + reg * e.ik_r[6 + n + i];
+        e.Mgrad[i] = -gi;
+        e.ik_active[i] = (e.ik_x[i] <= e.ik_lo[i] && gi > T(0)) || (e.ik_x[i] >= e.ik_hi[i] && gi < T(0));
+      }
+      g.sync();
+      KM_FOR(i, n) {
+        for (int j = 0; j <= i; j++) {
+          T s = 0;
+          if (e.ik_active[i] || e.ik_active[j]) s = i == j ? T(1) : T(0);
+          else {
+            for (int k = 0; k < 6; k++) s += e.ik_J[k][i] * e.ik_J[k][j];
+            if (i == j) s += lam + mu;
+          }
+          A[i * D::HS + j] = s;
+        }
+        if (e.ik_active[i]) e.Mgrad[i] = 0;
+      }
+      g.sync();
+      chol_factor<S, T, G>(A, e.Hd, n, D::HS, g);
+      chol_solve<S, T, G>(A, e.Hd, e.Mgrad, n, D::HS, g);
+      KM_FOR(i, n) {
+        const T xn = tclip(e.ik_x[i] + e.Mgrad[i], e.ik_lo[i], e.ik_hi[i]);
+        e.ik_xn[i] = xn;
+        e.qpos[m.arm_mask[a][i]] = xn;
+      }
+      g.sync();
+      kinematics<S, T, G>(e, m, g);
+      ik_residual<S, T, G>(e, m, g, a, e.ik_xn, e.ik_rn);
+      T cn = 0;
+      KM_FOR(k, nr) cn += T(0.5) * e.ik_rn[k] * e.ik_rn[k];
+      const T costn = g.sum(cn);
+      if (costn <= cost) {
+        KM_FOR(i, n) e.ik_x[i] = e.ik_xn[i];
+        KM_FOR(k, nr) e.ik_r[k] = e.ik_rn[k];
+        g.sync();
+        cost = costn;
+        ik_jacobian<S, T, G>(e, m, g, a);
+        mu = mu * T(0.25);
+        if (mu < T(1e-6)) mu = 0;
+      } else {
+        mu = mu == T(0) ? T(1e-4) : mu * T(4);
+      }
+    }
+  }
+  KM_FOR(i, n) {
+    const int j = m.arm_mask[a][i];
+    const float q = (float)tclip(e.ik_x[i], e.ik_lo[i], e.ik_hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
+    e.ctrl[j] = (T)q;
+    if (feasible && m.ik_teleport) e.qpos[j] = e.ik_x[i];
+    else e.qpos[j] = e.ik_qprev[i];
+  }
+  g.sync();
+}
+
+// scipy Rotation.from_matrix(R).as_euler("xyz") (extrinsic), then from_euler("xyz", e).as_quat()[[3,0,1,2]]
+template <typename T> KM_HD void mat_to_euler_xyz_ext(T* eul, const T* R) {
+  typedef Num<T> N;
+  eul[1] = N::asin(tclip(-R[6], T(-1), T(1)));
+  eul[0] = N::atan2(R[7], R[8]);
+  eul[2] = N::atan2(R[3], R[0]);
+}
+template <typename T> KM_HD void euler_xyz_ext_to_quat(T* q, const T* eul) {
+  typedef Num<T> N;
+  T s0, c0, s1, c1, s2, c2;
+  N::sincos(eul[0] * T(0.5), &s0, &c0);
+  N::sincos(eul[1] * T(0.5), &s1, &c1);
+  N::sincos(eul[2] * T(0.5), &s2, &c2);
+  const T qx[4] = {c0, s0, 0, 0}, qy[4] = {c1, 0, s1, 0}, qz[4] = {c2, 0, 0, s2};
+  T t[4];
+  qmul(t, qy, qx);
+  qmul(q, qz, t);
+}
+
+// KManipTask.before_step (reference env_sim.py:38-108); `act` points at this env's float32 action record
+KM_TPL KM_FN void before_step(KM_ARGS, const float* act) {
+  typedef Dim<S> D;
+  // ctrl passes through float32 (env_sim.py:40); the state already holds float32-representable values
+  KM_FOR(i, D::NU) e.ctrl[i] = (T)(float)e.ctrl[i];
+  g.sync();
+  // grippers (env_sim.py:41-59): both sliders follow slider 0, float32 arithmetic, clipped to EE_S_MIN/MAX
+  if (g.lane == 0) {
+    for (int a = 0; a < m.n_arm; a++)
+      if (m.off_grip[a] >= 0) {
+        float gv = act[m.off_grip[a]] * 0.0001f;
+        gv = (float)((double)gv + (double)e.qpos[m.arm_grip[a][0]]);
+        gv = gv < -0.029f ? -0.029f : (gv > 0.005f ? 0.005f : gv);
+        e.ctrl[m.arm_grip[a][0]] = (T)gv;
+        e.ctrl[m.arm_grip[a][1]] = (T)gv;
+      }
+  }
+  if (m.act_mode == 0) {
+    // end-effector targets (env_sim.py:60-70, 80-90) from the site poses of the last position stage
+    KM_FOR(a, m.n_arm) {
+      if (m.off_pos[a] < 0) continue;
+      T pos[3], mat[9], eul[3];
+      site_pose<S, T, G>(e, m, a, pos, mat);
+      for (int i = 0; i < 3; i++) e.ik_goal[a][i] = (T)((double)act[m.off_pos[a] + i] * 0.01) + pos[i];
+      mat_to_euler_xyz_ext(eul, mat);
+      for (int i = 0; i < 3; i++) eul[i] = (T)((double)act[m.off_orn[a] + i] * 0.1) + eul[i];
+      euler_xyz_ext_to_quat(e.ik_goal[a] + 3, eul);
+      for (int i = 0; i < 7; i++) e.mocap[7 * m.arm_mocap[a] + i] = e.ik_goal[a][i];
+    }
+    g.sync();
+    for (int a = 0; a < m.n_arm; a++)
+      if (m.off_pos[a] >= 0) ik_solve<S, T, G>(e, m, g, a);
+  } else {
+    // joint-position deltas (env_sim.py:100-103)
+    for (int a = 0; a < m.n_arm; a++) {
+      if (m.off_q[a] < 0) continue;
+      KM_FOR(i, m.arm_nmask[a]) {
+        const int j = m.arm_mask[a][i];
+        const float da = act[m.off_q[a] + i] * 0.1f;
+        e.ctrl[j] = (T)(float)((double)e.qpos[j] + (double)da);
+      }
+    }
+  }
+  g.sync();
+}
+
+// KManipTask.get_observation (reference env_sim.py:110-146): [q_pos, q_vel, cube_pos, cube_orn]
+KM_TPL KM_FN void observation(KM_ARGS) {
+  typedef Dim<S> D;
+  const T pi = T(3.14159265358979323846);
+  KM_FOR(i, D::OBS) {
+    T v;
+    if (i < D::QLEN) v = tclip((e.qpos[i] - m.range[i][0]) / (m.range[i][1] - m.range[i][0]), T(-1), T(1));
+    else if (i < 2 * D::QLEN) v = tclip(e.qvel[i - D::QLEN] / pi, T(-1), T(1));
+    else if (i < 2 * D::QLEN + 3) {
+      const int k = i - 2 * D::QLEN;
+      v = tclip((e.qpos[D::NVA + k] - m.spawn_lo[k]) / (m.spawn_hi[k] - m.spawn_lo[k]), T(-1), T(1));
+    } else v = e.qpos[D::NVA + 3 + (i - 2 * D::QLEN - 3)];
+    e.obs[i] = v;
+  }
+  g.sync();
+}
+
+// KManipTask.get_reward (reference env_sim.py:148-179).  The touch/lift bonuses are unreachable in the shipped
+// model; *flags reports what the contact scan saw: bit0 cube-table, bit1 right pads, bit2 left pads.
+KM_TPL KM_FN T reward(KM_ARGS, int* flags) {
+  typedef Dim<S> D;
+  typedef Num<T> N;
+  T vn = 0;
+  KM_FOR(i, D::NV) vn += e.qvel[i] * e.qvel[i];
+  T r = -T(0.01) * N::sqrt(g.sum(vn));
+  for (int a = m.n_arm - 1; a >= 0; a--) {
+    if (m.off_grip[a] < 0) continue;
+    T pos[3], mat[9];
+    site_pose<S, T, G>(e, m, a, pos, mat);
+    const T d[3] = {e.qpos[D::NVA] - pos[0], e.qpos[D::NVA + 1] - pos[1], e.qpos[D::NVA + 2] - pos[2]};
+    r += T(0.01) * (T(1) / (N::sqrt(dot3(d, d)) + T(1e-6)));
+  }
+  int f = 0;
+  for (int c = 0; c < e.ncon; c++) {
+    const int s = e.con_slot[c];
+    f |= s >= D::NPAD ? 1 : (m.pad_arm[s] == 0 ? 2 : 4);
+  }
+  *flags = f;
+  return r;
+}
+
+// KManipTask.initialize_episode (reference env_sim.py:23-36) with a counter-based device RNG for the cube spawn
+KM_TPL KM_FN void reset_state(KM_ARGS, uint64_t seed, uint64_t env_id, const T* cube_xyz) {
+  typedef Dim<S> D;
+  KM_FOR(i, D::NV) { e.qvel[i] = 0; e.warm[i] = 0; }
+  KM_FOR(i, D::NVA) {
+    const T v = i < D::QLEN ? m.q_home[i] : T(0);
+    e.qpos[i] = v; e.ctrl[i] = v;
+  }
+  KM_FOR(i, D::NMOCAP * 7) e.mocap[i] = m.mocap0[i];
+  if (g.lane == 0) {
+    if (cube_xyz) { for (int i = 0; i < 3; i++) e.qpos[D::NVA + i] = cube_xyz[i]; }
+    else {
+      double u[3];
+      spawn_uniforms(seed, env_id, (uint32_t)e.episode, u);
+      for (int i = 0; i < 3; i++) e.qpos[D::NVA + i] = (T)(m.spawn_lo_d[i] + u[i] * (m.spawn_hi_d[i] - m.spawn_lo_d[i]));
+    }
+    for (int i = 0; i < 4; i++) e.qpos[D::NVA + 3 + i] = m.cube_quat0[i];
+    e.time = 0; e.step = 0;
+  }
+  g.sync();
+}
+
+// one-time set-up of the parts of the working set that never change
+KM_TPL KM_FN void init_env(KM_ARGS) {
+  typedef Dim<S> D;
+  KM_FOR(w, D::NVA * D::NVA) (&e.M[0][0])[w] = 0;
+  KM_FOR(r, D::NFRIC) {
+    e.efc_desc[r] = efc_pack(EFC_FRICTION, m.fric_dof[r], 0, 0);
+    e.efc_R[r] = m.fr_R[r]; e.efc_D[r] = m.fr_D[r]; e.efc_B[r] = m.fr_B[r]; e.efc_Kip[r] = 0; e.efc_floss[r] = m.fr_loss[r];
+  }
+  if (g.lane == 0) { e.ls_evals = 0; e.solver_niter = 0; e.ncon = 0; e.nlim = 0; e.nefc = D::NFRIC; }
+  g.sync();
+}
+
+// Outputs of one env step (any pointer may be null)
+template <typename T> struct StepOut {
+  T* obs; T* final_obs; T* reward; unsigned char* truncated; unsigned char* terminated;
+  int* con_flags; int* ncon; int* con_geoms; int con_cap;
+};
+
+// One env step on the working set already holding the env's state.
+KM_TPL KM_FN void env_step(KM_ARGS, const float* act, const StepOut<T>& o, long env, int autoreset, uint64_t seed,
+                           uint64_t env0) {
+  typedef Dim<S> D;
+  step1<S, T, G>(e, m, g);
+  before_step<S, T, G>(e, m, g, act);
+  step2<S, T, G>(e, m, g);
+  for (int s = 1; s < m.nsub; s++) { step1<S, T, G>(e, m, g); step2<S, T, G>(e, m, g); }
+  // closing mj_step1: only kinematics and collision feed the reward / contact report; the next env step
+  // recomputes the full position and velocity stages from the stored state
+  kinematics<S, T, G>(e, m, g);
+  collision<S, T, G>(e, m, g);
+  int fl;
+  const T r = reward<S, T, G>(e, m, g, &fl);
+  observation<S, T, G>(e, m, g);
+  if (o.obs) KM_FOR(i, D::OBS) o.obs[env * D::OBS + i] = e.obs[i];
+  if (g.lane == 0) {
+    if (o.reward) o.reward[env] = r;
+    if (o.con_flags) o.con_flags[env] = fl;
+    if (o.ncon) o.ncon[env] = e.ncon;
+    if (o.con_geoms)
+      for (int c = 0; c < o.con_cap; c++) {
+        int g1 = -1, g2 = -1;
+        if (c < e.ncon) { const int s = e.con_slot[c]; g1 = s < D::NPAD ? m.pad_geom[s] : m.table_geom; g2 = m.cube_geom; }
+        o.con_geoms[env * 2 * o.con_cap + 2 * c] = g1;
+        o.con_geoms[env * 2 * o.con_cap + 2 * c + 1] = g2;
+      }
+    e.step += 1;
+  }
+  g.sync();
+  const bool trunc = e.step >= m.max_episode_steps;
+  if (g.lane == 0) {
+    if (o.truncated) o.truncated[env] = trunc ? 1 : 0;
+    if (o.terminated) o.terminated[env] = 0;   // the reference never terminates
+  }
+  if (autoreset && trunc) {
+    // same-step autoreset: final_obs keeps the last observation of the finished episode
+    if (o.final_obs) KM_FOR(i, D::OBS) o.final_obs[env * D::OBS + i] = e.obs[i];
+    if (g.lane == 0) e.episode += 1;
+    g.sync();
+    reset_state<S, T, G>(e, m, g, seed, env0 + (uint64_t)env, (const T*)0);
+    observation<S, T, G>(e, m, g);
+    if (o.obs) KM_FOR(i, D::OBS) o.obs[env * D::OBS + i] = e.obs[i];
+  }
+  g.sync();
+}
+
+}  // namespace km

@@ -1,0 +1,150 @@
+/* kmanip_b200.h -- C-ABI of the B200 batched simulator for the gym-kmanip env-step hot path.
+ *
+ * This is the drop-in boundary.  The reference selects a simulation backend through the seam
+ *     gym_kmanip/env_base.py:192-200   self.env = new(self)
+ * and talks to it through
+ *     gym_kmanip/env_sim.py:187-203    k_reset() / k_step(action) / k_render(cam) / k_close()
+ * (each returning (terminated, reward, discount, observation, sim_time)).  The entry points below are what a
+ * replacement backend binds for that seam, batched over n_envs independent environments:
+ *
+ *   km_create / km_destroy   <- env_sim.py:206-211  new(): Physics.from_xml_path + KManipTask + control.Environment
+ *                               (the MJCF is flattened on the host; the library receives plain arrays)
+ *   km_reset                 <- env_sim.py:190-194  k_reset -> KManipTask.initialize_episode (env_sim.py:23-36)
+ *   km_step                  <- env_sim.py:196-200  k_step  -> before_step (:38-108, incl. ik_mujoco.py:100-155),
+ *                               physics.step(10), get_reward (:148-179), get_observation (:110-146);
+ *                               truncation after max_episode_steps = gymnasium TimeLimit of __init__.py:28,247
+ *   km_get_state/km_set_state<- callers reaching through env.unwrapped.env.physics.data.{qpos,qvel,ctrl,mocap_pos,mocap_quat,time}
+ *                               (examples/1_control.py:26, examples/2_synthetic_data.py:33-34, examples/4_teleop.py:77-83)
+ *   km_contacts              <- the contact scan of get_reward (env_sim.py:166-174)
+ *   km_step_host / km_reset_host: the same calls with HOST buffers (copies inside), what a ctypes/cgo-style
+ *                               binding that owns no device memory would call.
+ *
+ * Conventions: every call returns 0 on success or a negative error code, with a thread-local message from
+ * km_last_error().  The library never owns caller buffers.  Device pointers must live on the handle's device.
+ * Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream) except the
+ * *_host variants, which synchronise before returning.  One handle per device; calls on one handle must be
+ * serialised by the caller; handles on different devices are independent (env sharding needs no collective).
+ *
+ * Record layouts (env-major, one contiguous record per env -- the coalesced layout for lane-group-per-env kernels):
+ *   state    qpos[nq] qvel[nv] ctrl[nu] qacc_warmstart[nv] mocap[7*nmocap] time   (dtype of the handle: f32 or f64)
+ *   action   float32[act_dim], keys concatenated in the order of env_base.py:149-190
+ *   obs      [q_pos(q_len) q_vel(q_len) cube_pos(3) cube_orn(4)]                    (dtype of the handle)
+ */
+#ifndef KMANIP_B200_H
+#define KMANIP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Flat model: mjModel-named arrays produced by gym_kmanip_b200/mjcf.py (host pointers, copied at km_create). */
+typedef struct km_model {
+  int nbody, njnt, nq, nv, nu, nsite, ngeom, npair, nmocap;
+  int iterations, ls_iterations;
+  double timestep, gravity[3], tolerance, ls_tolerance, impratio, meaninertia;
+  const int *body_parent, *body_rootid, *body_mocapid, *body_jntadr, *body_jntnum;
+  const double *body_pos, *body_quat, *body_mass, *body_ipos, *body_inertia, *body_invweight0;
+  const int *jnt_type, *jnt_bodyid, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
+  const double *jnt_pos, *jnt_axis, *jnt_range, *jnt_solref, *jnt_solimp, *qpos0;
+  const int *dof_bodyid, *dof_jntid, *dof_parentid;
+  const double *dof_frictionloss, *dof_solref, *dof_solimp, *dof_invweight0;
+  const int *act_jntid, *act_ctrllimited, *act_forcelimited;
+  const double *act_kp, *act_ctrlrange, *act_forcerange;
+  const int *site_bodyid;
+  const double *site_pos, *site_quat;
+  const int *geom_type, *geom_bodyid;
+  const double *geom_pos, *geom_quat, *geom_size;
+  const int *pair_geom1, *pair_geom2, *pair_condim;
+  const double *pair_friction, *pair_solref, *pair_solimp, *pair_margin;
+  const double *mocap_pos0, *mocap_quat0;
+} km_model;
+
+/* Task: the KManipTask configuration of one registered env id (env_sim.py:18-179, __init__.py:28-208). */
+#define KM_MAXARM 2
+#define KM_MAXMASK 8
+typedef struct km_task {
+  int q_len, n_arm, act_dim;
+  int act_mode;                          /* 0: end-effector targets -> IK; 1: joint-position deltas */
+  int arm_nmask[KM_MAXARM];
+  int arm_mask[KM_MAXARM][KM_MAXMASK];   /* q_id_{r,l}_mask */
+  int arm_grip[KM_MAXARM][2];            /* ctrl_id_{r,l}_grip */
+  int arm_site[KM_MAXARM], arm_eebody[KM_MAXARM], arm_mocap[KM_MAXARM];
+  int off_pos[KM_MAXARM], off_orn[KM_MAXARM], off_grip[KM_MAXARM], off_q[KM_MAXARM];
+  int cube_body, cube_qposadr;
+  int ik_iters, ik_teleport, max_episode_steps;
+  double q_home[32], cube_spawn_lo[3], cube_spawn_hi[3];
+} km_task;
+
+typedef struct km_sim* km_handle;
+
+enum { KM_F32 = 32, KM_F64 = 64 };
+enum { KM_SCENE_SOLO_ARM = 0, KM_SCENE_DUAL_ARM = 1, KM_SCENE_TORSO = 2 };
+enum { KM_OK = 0, KM_ERR_ARG = -1, KM_ERR_MODEL = -2, KM_ERR_CUDA = -3, KM_ERR_NODEVICE = -4 };
+
+/* Optional outputs of km_step (device pointers; any may be NULL). */
+typedef struct km_step_out {
+  void* obs;                 /* [n][obs_dim]  observation after the step (first obs of the new episode on autoreset) */
+  void* final_obs;           /* [n][obs_dim]  last observation of the finished episode, written only where truncated */
+  void* reward;              /* [n] */
+  unsigned char* truncated;  /* [n] 1 on the max_episode_steps-th step since reset */
+  unsigned char* terminated; /* [n] always 0 (the reference never terminates) */
+  int* con_flags;            /* [n] bit0 cube-table, bit1 right finger pads, bit2 left finger pads */
+  int* ncon;                 /* [n] */
+  int* con_geoms;            /* [n][2*km_max_contacts] (geom1, geom2) per contact, -1 padded */
+} km_step_out;
+
+const char* km_last_error(void);
+const char* km_version(void);
+
+/* scene: KM_SCENE_*; dtype: KM_F32 / KM_F64; seed/env0: cube-spawn RNG key and the global id of env 0 of this shard. */
+int km_create(const km_model* model, const km_task* task, int scene, int n_envs, int device, int dtype,
+              uint64_t seed, uint64_t env0, km_handle* out);
+void km_destroy(km_handle h);
+
+int km_nq(km_handle h);
+int km_nv(km_handle h);
+int km_nu(km_handle h);
+int km_nmocap(km_handle h);
+int km_obs_dim(km_handle h);
+int km_act_dim(km_handle h);
+int km_state_dim(km_handle h);        /* scalars per state record */
+int km_max_contacts(km_handle h);
+int km_num_envs(km_handle h);
+int km_dtype(km_handle h);
+/* launch configuration: lanes per env (8/16/32) and envs per CTA; 0 keeps the current value */
+int km_configure(km_handle h, int lanes_per_env, int envs_per_block);
+long long km_launch_count(km_handle h);   /* kernels launched by this handle so far */
+int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* grid, int* ctas_per_sm, int* smem_bytes);
+
+/* Episode reset.  mask_dev: [n] uint8, NULL = all envs.  cube_xyz_dev: [n][3] (dtype of the handle), NULL = device
+   RNG Philox4x32-10(seed, env0 + i, episode).  obs_dev: optional [n][obs_dim]. */
+int km_reset(km_handle h, const unsigned char* mask_dev, const void* cube_xyz_dev, void* obs_dev, void* stream);
+
+/* One env step of every env (10 physics sub-steps).  action_dev: [n][act_dim] float32.  autoreset != 0 resets
+   truncated envs inside the same launch. */
+int km_step(km_handle h, const float* action_dev, const km_step_out* out, int autoreset, void* stream);
+
+/* Teacher-forced access to the full state (device buffers of the handle's dtype, record layout above).
+   step_count / episode: optional [n] int32. */
+int km_get_state(km_handle h, void* state_dev, int* step_count_dev, int* episode_dev, void* stream);
+int km_set_state(km_handle h, const void* state_dev, const int* step_count_dev, const int* episode_dev, void* stream);
+/* Pointer to the library-owned state buffer ([n][km_state_dim], dtype of the handle) for zero-copy views. */
+void* km_state_ptr(km_handle h);
+
+/* Contacts of the most recent step: runs the position stage on the stored state. */
+int km_contacts(km_handle h, int* ncon_dev, int* con_geoms_dev, void* stream);
+
+/* Diagnostics of the most recent step's last sub-step: [n] Newton iterations, [n] line-search evaluations (cumulative). */
+int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream);
+
+/* Host-buffer variants (pageable or pinned host memory; copies and a stream synchronise inside). */
+int km_reset_host(km_handle h, const unsigned char* mask, const void* cube_xyz, void* obs);
+int km_step_host(km_handle h, const float* action, void* obs, void* reward, unsigned char* truncated, int autoreset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,36 @@
+"""Shared helpers of the parity tests: the relative-error metric and oracle-side batch rollouts."""
+import numpy as np
+
+from oracle import oracle as orc_mod
+
+
+def rel_err(a, b, floor=1e-3):
+    """max |a - b| / max(|b|, floor) over one field of one batch (the scale is the field's own magnitude)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), floor))
+
+
+def pack_state(st):
+    n = st["qpos"].shape[0]
+    return np.concatenate([st["qpos"], st["qvel"], st["ctrl"], st["warm"], st["mocap"][:, : max(st["mocap"].shape[1], 0)],
+                           st["time"].reshape(n, 1)], axis=1)
+
+
+def oracle_rollout(env_id, n, steps, seed=0, action_seed=1, nthreads=0, **okw):
+    """Free-running oracle rollout of n envs; returns the list of (state_before, action, outputs, state_after)."""
+    o = orc_mod.Oracle(env_id, **okw)
+    st = orc_mod.batch_reset_state(o, n, seed=seed)
+    if o.nmocap == 0:
+        st["mocap"] = np.zeros((n, 0))
+    rng = np.random.default_rng(action_seed)
+    out = []
+    for _ in range(steps):
+        a = rng.uniform(-1, 1, (n, o.task.act_dim)).astype(np.float32)
+        before = {k: v.copy() for k, v in st.items()}
+        obs, fobs, rew, trunc, flags, ncon, geoms = orc_mod.batch_step(o, st, a, autoreset=True, seed=seed, nthreads=nthreads)
+        after = {k: v.copy() for k, v in st.items()}
+        out.append(dict(before=before, action=a, obs=obs, final_obs=fobs, reward=rew, truncated=trunc, flags=flags, ncon=ncon,
+                        geoms=geoms, after=after))
+    return o, out

@@ -1,0 +1,62 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle from identical states (teacher-forced).
+
+Tolerances (relative to each field's own magnitude over the batch, parity_util.rel_err):
+  fp64 build: 1e-10 per env step (BASELINE.json north_star)
+  fp32 build: 1e-5 is the north_star figure for one physics sub-step; an env step chains 10 sub-steps of a stiff
+              servo system (kp = 1000, h^2 w^2 ~ 0.8), so the per-env-step bound asserted here is 2e-4 on
+              velocities / 2e-5 on positions; contact-pair indices and done flags are bit-exact.
+"""
+import numpy as np
+import pytest
+
+from parity_util import oracle_rollout, pack_state, rel_err
+
+ENVS = ["KManipSoloArmQPos", "KManipSoloArm", "KManipDualArm", "KManipDualArmQPos", "KManipTorso"]
+
+
+def _run(env_id, dtype, n, steps, tol_pos, tol_vel, tol_obs):
+    import torch
+    from gym_kmanip_b200.batch_sim import BatchSim
+    o, traj = oracle_rollout(env_id, n, steps, seed=3, action_seed=5)
+    sim = BatchSim(env_id, n, dtype=dtype, seed=3)
+    sl = sim.state_slices()
+    worst = {}
+    for t, rec in enumerate(traj):
+        b = rec["before"]
+        sim.set_state(pack_state(b), step=b["step"], episode=b["episode"])
+        act = torch.from_numpy(rec["action"]).cuda()
+        obs, rew, term, trunc = sim.step(act, autoreset=True)
+        torch.cuda.synchronize()
+        st, stepc, ep = sim.get_state()
+        st = st.double().cpu().numpy()
+        a = rec["after"]
+        errs = dict(qpos=rel_err(st[:, sl["qpos"]], a["qpos"]), qvel=rel_err(st[:, sl["qvel"]], a["qvel"]),
+                    ctrl=rel_err(st[:, sl["ctrl"]], a["ctrl"]), obs=rel_err(obs.double().cpu().numpy(), rec["obs"]),
+                    reward=rel_err(rew.double().cpu().numpy(), rec["reward"]))
+        for k, v in errs.items():
+            worst[k] = max(worst.get(k, 0.0), v)
+        # bit-exact integer outputs
+        assert np.array_equal(trunc.cpu().numpy(), rec["truncated"]), f"truncated differs at step {t}"
+        assert not term.any()
+        assert np.array_equal(stepc.cpu().numpy(), a["step"]) and np.array_equal(ep.cpu().numpy(), a["episode"])
+        assert np.array_equal(sim.ncon.cpu().numpy(), rec["ncon"]), f"ncon differs at step {t}"
+        mc = sim.max_contacts
+        assert np.array_equal(sim.con_geoms.cpu().numpy(), rec["geoms"][:, : 2 * mc]), f"contact pairs differ at step {t}"
+        assert np.array_equal(sim.con_flags.cpu().numpy(), rec["flags"])
+    print(env_id, dtype, {k: "%.2e" % v for k, v in worst.items()})
+    assert worst["qpos"] < tol_pos and worst["ctrl"] < tol_pos, worst
+    assert worst["qvel"] < tol_vel, worst
+    assert worst["obs"] < tol_obs and worst["reward"] < tol_obs, worst
+    assert sim.launches >= steps
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", ENVS)
+def test_env_step_parity_fp64(env_id):
+    _run(env_id, "float64", n=64, steps=70, tol_pos=1e-10, tol_vel=1e-10, tol_obs=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", ENVS)
+def test_env_step_parity_fp32(env_id):
+    _run(env_id, "float32", n=64, steps=70, tol_pos=2e-5, tol_vel=2e-4, tol_obs=2e-4)
