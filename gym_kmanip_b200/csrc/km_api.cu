@@ -54,20 +54,22 @@ struct DeviceGuard {
 
 static int configure(km_sim* h, int G, int epb) {
   if (G == 0) G = h->G;
-  if (G != 8 && G != 16 && G != 32) return fail(KM_ERR_ARG, "lanes_per_env must be 8, 16 or 32");
+  if ((G != 16 && G != 32) || G < h->vt.nlanes_min) return fail(KM_ERR_ARG, "lanes_per_env must be 16 or 32 and at least the number of dofs");
   int dev_smem = 0;
   KM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   const size_t model_b = (h->vt.model_bytes + 15) / 16 * 16;
+  const int fit = (int)(((size_t)dev_smem - model_b) / h->vt.env_bytes);
+  const int cap = fit * G > h->vt.max_threads ? h->vt.max_threads / G : fit;
   if (epb == 0) {
-    // default: the largest CTA that still leaves room for two CTAs per SM (shared memory is the limiter)
-    int sm_total = 0;
-    KM_CUDA(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-    const size_t per_cta = (size_t)sm_total / 2 - 1024;
-    epb = (int)((per_cta - model_b) / h->vt.env_bytes);
-    if (epb * G > 512) epb = 512 / G;
-    if (epb < 1) epb = (int)(((size_t)dev_smem - model_b) / h->vt.env_bytes);
+    // default: one CTA per SM holding as many envs as shared memory allows, shrunk so that the waves are balanced
+    // (4096 envs on 148 SMs -> 28 envs per CTA, a single wave)
+    if (cap < 1) return fail(KM_ERR_ARG, "an env does not fit in shared memory");
+    const long per_wave = (long)h->num_sms * cap;
+    const long waves = ((long)h->n + per_wave - 1) / per_wave;
+    epb = (int)(((long)h->n + h->num_sms * waves - 1) / (h->num_sms * waves));
+    if (epb > cap) epb = cap;
   }
-  if (epb < 1 || epb * G > 512) return fail(KM_ERR_ARG, "envs_per_block out of range (1 .. 512 / lanes_per_env)");
+  if (epb < 1 || epb > cap) return fail(KM_ERR_ARG, "envs_per_block out of range for this scene / precision");
   if (model_b + (size_t)epb * h->vt.env_bytes > (size_t)dev_smem)
     return fail(KM_ERR_ARG, "envs_per_block needs more shared memory than a CTA can opt in to");
   int ctas = 0;
@@ -121,6 +123,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   if (h->vt.fill(model, task, host_model.data(), err) != 0) { delete h; return fail(KM_ERR_MODEL, err); }
   DeviceGuard guard(device);
   if (!guard.ok) { delete h; return fail(KM_ERR_CUDA, "km_create: cudaSetDevice failed"); }
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   cudaError_t e;
   const size_t sb = h->vt.scalar_bytes, n = (size_t)n_envs;
 #define KM_ALLOC(ptr, bytes) if ((e = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) { km_destroy(h); return cuda_fail(e, "cudaMalloc"); }
@@ -146,8 +149,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
     km_destroy(h);
     return cuda_fail(e, "km_create: initialisation");
   }
-  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
-  h->G = h->vt.nv <= 16 ? 16 : 32;
+  h->G = 32;   // one env per warp: literal full-warp masks, no divergence between envs sharing a warp
   int rc = configure(h, h->G, 0);
   if (rc != KM_OK) { km_destroy(h); return rc; }
   *out = h;

@@ -1,6 +1,6 @@
 // km_common.cuh -- scalar traits, small vector/quaternion algebra and the lane-group primitives.
 //
-// Execution model of the whole simulator: one *group* of G lanes (G = 8/16/32, all inside one warp)
+// Execution model of the whole simulator: one *group* of G lanes (G = 16 or 32, all inside one warp, one lane per dof)
 // owns one environment whose working set lives in shared memory.  Code is written as bulk-synchronous
 // phases: `KM_FOR(i, n)` distributes n independent items over the lanes, `g.sync()` separates phases,
 // `g.sum()` is a butterfly reduction that leaves the bit-identical result in every lane, so scalar
@@ -13,9 +13,10 @@
 #include <cmath>
 #include <cstdint>
 
+#include <type_traits>
 #if defined(__CUDACC__)
 #define KM_HD __host__ __device__ __forceinline__
-#define KM_FN __host__ __device__
+#define KM_FN __host__ __device__ __noinline__
 #else
 #define KM_HD inline
 #define KM_FN
@@ -32,11 +33,36 @@ template <> struct Num<float> {
   static KM_HD float asin(float x) { return asinf(x); }
   static KM_HD float tan(float x) { return tanf(x); }
   static KM_HD float pow(float x, float y) { return powf(x, y); }
+  // sin/cos for |x| up to a few turns (half joint angles, Euler half angles): quadrant reduction with a
+  // two-term Cody-Waite pi/2 and the usual degree-7/8 minimax kernels; ~1 ulp, no large-argument slow path
+  // (the library sincosf drags a Payne-Hanek path with a local-memory table into every call site).
   static KM_HD void sincos(float x, float* s, float* c) {
 #if defined(__CUDA_ARCH__)
-    sincosf(x, s, c);
+    const float q = rintf(x * 0.636619772367581343f);
+    float r = fmaf(q, -1.57079601287841796875f, x);
+    r = fmaf(q, -3.1391647326017846e-7f, r);
+    r = fmaf(q, -5.3903025299577648e-15f, r);
+    const int n = (int)q;
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+    sp = fmaf(sp, r2, -1.66666546e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+    cp = fmaf(cp, r2, 4.16666457e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    cp = fmaf(cp, r2, 1.0f);
+    const float ss = (n & 1) ? cp : sp, cc = (n & 1) ? sp : cp;
+    *s = (n & 2) ? -ss : ss;
+    *c = ((n + 1) & 2) ? -cc : cc;
 #else
     *s = sinf(x); *c = cosf(x);
+#endif
+  }
+  static KM_HD float rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
 #endif
   }
   static KM_HD float eps() { return 1.1920929e-7f; }
@@ -57,6 +83,7 @@ template <> struct Num<double> {
     *s = ::sin(x); *c = ::cos(x);
 #endif
   }
+  static KM_HD double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   static KM_HD double eps() { return 2.220446049250313e-16; }
   static KM_HD double minval() { return 1e-15; }
   static KM_HD double huge() { return 1.0e300; }
@@ -69,27 +96,53 @@ template <typename T> KM_HD T tclip(T x, T lo, T hi) { return x < lo ? lo : (x >
 template <int G> struct Grp {
   int lane;        // 0..G-1 inside the group
   unsigned mask;   // the group's lanes inside its warp
+  unsigned wmask;  // lanes to reconverge with: the whole warp while every group of the warp runs an env, else `mask`
+  // Groups sharing a warp run data-dependent loops (Newton, line search) and would otherwise stay diverged,
+  // halving the issue efficiency of everything that follows; converge() is placed after such loops.
+  // a whole-warp group names its lanes with a literal mask: the compiler then emits bare SHFL / no WARPSYNC
+  KM_HD unsigned lanes() const { return G == 32 ? 0xffffffffu : mask; }
+  KM_HD void converge() const {
+#if defined(__CUDA_ARCH__)
+    if (G < 32) __syncwarp(wmask);
+#endif
+  }
+  template <typename T> KM_HD T shfl(T v, int src) const {
+#if defined(__CUDA_ARCH__)
+    return __shfl_sync(lanes(), v, src, G);
+#else
+    return v;
+#endif
+  }
   KM_HD void sync() const {
 #if defined(__CUDA_ARCH__)
-    __syncwarp(mask);
+    __syncwarp(lanes());
 #endif
   }
   template <typename T> KM_HD T sum(T v) const {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(lanes(), v, o, G);
 #endif
     return v;
   }
   KM_HD bool any(bool p) const {
 #if defined(__CUDA_ARCH__)
-    return (__ballot_sync(mask, p) & mask) != 0u;
+    return (__ballot_sync(lanes(), p) & lanes()) != 0u;
 #else
     return p;
 #endif
   }
 };
 #define KM_FOR(i, n) for (int i = g.lane; i < (n); i += G)
+
+// compile-time loops (bodies receive std::integral_constant so indices can select registers / if constexpr)
+template <int I> using IC = std::integral_constant<int, I>;
+template <int I, int N, class F> KM_HD void sfor(F&& f) {
+  if constexpr (I < N) { f(IC<I>{}); sfor<I + 1, N>(static_cast<F&&>(f)); }
+}
+template <int N, class F> KM_HD void sfor_rev(F&& f) {
+  if constexpr (N > 0) { f(IC<N - 1>{}); sfor_rev<N - 1>(static_cast<F&&>(f)); }
+}
 
 // ---------------------------------------------------------------------------------------- 3-vectors, quaternions (wxyz)
 template <typename T> KM_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }

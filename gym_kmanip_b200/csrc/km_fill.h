@@ -96,6 +96,7 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
     m.lim_invw[l] = (T)fm->dof_invweight0[l];
     for (int i = 0; i < 2; i++) m.lim_solref[l][i] = (T)fm->jnt_solref[2 * l + i];
     for (int i = 0; i < 5; i++) m.lim_solimp[l][i] = (T)fm->jnt_solimp[5 * l + i];
+    KM_FILL_CHECK(fm->jnt_solimp[5 * l + 4] == 2 || fm->jnt_solimp[5 * l + 4] == 1, "solimp power must be 1 or 2");
     m.lim_solimp[l][5] = (T)(1.0 - fm->jnt_solimp[5 * l]); m.lim_solimp[l][6] = (T)(1.0 - fm->jnt_solimp[5 * l + 1]);
     KM_FILL_CHECK(fm->body_rootid[b] == fm->body_rootid[fm->jnt_bodyid[0]], "all links share one tree root");
   }
@@ -112,6 +113,8 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
     for (int c = e; c < D::NVA; c++) KM_FILL_CHECK(!((m.ancmask[c] >> l) & 1u), "subtrees must be contiguous (depth-first numbering)");
     m.sub_end[l] = e;
   }
+  for (int i = 0, w = 0; i < D::NV; i++)
+    for (int j = 0; j <= i; j++) m.pair_ij[w++] = (unsigned short)(i << 8 | j);
   int maxd = 0;
   for (int l = 0; l < D::NVA; l++) maxd = depth[l] > maxd ? depth[l] : maxd;
   KM_FILL_CHECK(maxd + 1 <= D::MAXLEVEL, "kinematic tree too deep");
@@ -133,6 +136,7 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
   }
   // ---- friction-loss rows (pos = 0: impedance, regulariser and damping gain are constants)
   int nf = 0;
+  for (int d = 0; d < D::NV; d++) m.dof_fric[d] = -1;
   for (int d = 0; d < fm->nv; d++) {
     if (!(fm->dof_frictionloss[d] > 0)) continue;
     KM_FILL_CHECK(nf < D::NFRIC, "friction-loss row count");
@@ -142,8 +146,8 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
     const double imp = impedance<double>(si, 0.0, &omi);
     const double R = std::fmax(1e-15, omi * fm->dof_invweight0[d] / imp);
     const double tc = std::fmax(fm->dof_solref[2 * d], 2.0 * fm->timestep);
-    m.fric_dof[nf] = d; m.fr_loss[nf] = (T)fm->dof_frictionloss[d];
-    m.fr_R[nf] = (T)R; m.fr_D[nf] = (T)(1.0 / R); m.fr_B[nf] = (T)(2.0 / (si[1] * tc));
+    m.fric_dof[nf] = d; m.dof_fric[d] = nf; m.fr_loss[nf] = (T)fm->dof_frictionloss[d];
+    m.fr_R[nf] = (T)R; m.fr_Rf[nf] = (T)(R * fm->dof_frictionloss[d]); m.fr_D[nf] = (T)(1.0 / R); m.fr_B[nf] = (T)(2.0 / (si[1] * tc));
     nf++;
   }
   KM_FILL_CHECK(nf == D::NFRIC, "friction-loss row count");
@@ -153,6 +157,7 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
     const int g1 = fm->pair_geom1[p], g2 = fm->pair_geom2[p];
     KM_FILL_CHECK(fm->geom_bodyid[g2] == cube_b && fm->geom_type[g2] == 6, "geom2 of every pair is the cube box");
     KM_FILL_CHECK(fm->pair_condim[p] == 4 && fm->pair_margin[p] == 0, "condim 4, margin 0");
+    KM_FILL_CHECK(fm->pair_solimp[5 * p + 4] == 2 || fm->pair_solimp[5 * p + 4] == 1, "solimp power must be 1 or 2");
     const int b1 = fm->geom_bodyid[g1];
     const double tran = fm->body_invweight0[2 * b1] + fm->body_invweight0[2 * cube_b];
     const double rot = fm->body_invweight0[2 * b1 + 1] + fm->body_invweight0[2 * cube_b + 1];

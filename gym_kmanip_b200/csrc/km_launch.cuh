@@ -38,7 +38,7 @@ struct KmArgs {
 
 struct KmVtable {
   size_t model_bytes, env_bytes, scalar_bytes;
-  int nq, nv, nu, nmocap, obs_dim, state_dim, maxcon, nlanes_min;
+  int nq, nv, nu, nmocap, obs_dim, state_dim, maxcon, nlanes_min, max_threads;
   int (*fill)(const km_model*, const km_task*, void* dst, std::string& err);
   cudaError_t (*step)(const KmArgs&);
   cudaError_t (*reset)(const KmArgs&);
@@ -52,11 +52,18 @@ struct KmVtable {
 template <class S, typename T> constexpr size_t model_smem() { return (sizeof(Model<S, T>) + 15) / 16 * 16; }
 template <class S, typename T> constexpr size_t env_smem() { return (sizeof(Env<S, T>) + 15) / 16 * 16; }
 template <class S, typename T> size_t smem_bytes(int epb) { return model_smem<S, T>() + (size_t)epb * env_smem<S, T>(); }
+// most envs one CTA can hold in the 227 KB of opt-in shared memory (one warp each at G = 32), and the thread bound
+// the kernels are compiled for (it caps registers so that such a CTA is resident: 65536 / threads)
+template <class S, typename T> constexpr int max_epb() {
+  return (int)((232448 - model_smem<S, T>()) / env_smem<S, T>()) > 32 ? 32 : (int)((232448 - model_smem<S, T>()) / env_smem<S, T>());
+}
+template <class S, typename T> constexpr int max_threads() { return 32 * max_epb<S, T>(); }
 
 template <int G> __device__ __forceinline__ Grp<G> make_group() {
   Grp<G> g;
   g.lane = threadIdx.x % G;
   g.mask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (((threadIdx.x & 31) / G) * G));
+  g.wmask = g.mask;
   return g;
 }
 
@@ -87,15 +94,23 @@ template <class S, typename T, int G> __device__ __forceinline__ void store_stat
   if (g.lane == 0) { a.step[env] = e.step; a.episode[env] = e.episode; }
 }
 
-template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_env_step(KmArgs a) {
+template <class S, typename T, int G> __global__ void __launch_bounds__(max_threads<S, T>()) k_env_step(KmArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Model<S, T>& m = stage_model<S, T>(smem, a.model);
-  const Grp<G> g = make_group<G>();
+  Grp<G> g = make_group<G>();
   const int slot = threadIdx.x / G;
   Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
   init_env<S, T, G>(e, m, g);
   StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON};
-  for (long env = (long)blockIdx.x * a.epb + slot; env < a.n; env += (long)gridDim.x * a.epb) {
+  // every warp walks the same number of tiles so that the groups sharing a warp can reconverge
+  for (long tile = (long)blockIdx.x * a.epb; tile < a.n; tile += (long)gridDim.x * a.epb) {
+    const long env = tile + slot;
+    const bool valid = env < a.n;
+    if (G < 32) {
+      __syncwarp();
+      g.wmask = __all_sync(0xffffffffu, valid) ? 0xffffffffu : g.mask;
+    }
+    if (!valid) continue;
     load_state<S, T, G>(e, a, env, g);
     env_step<S, T, G>(e, m, g, a.act + env * m.act_dim, o, env, a.autoreset, a.seed, a.env0);
     store_state<S, T, G>(e, a, env, g);
@@ -107,7 +122,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_e
   }
 }
 
-template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_reset(KmArgs a) {
+template <class S, typename T, int G> __global__ void __launch_bounds__(max_threads<S, T>()) k_reset(KmArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Model<S, T>& m = stage_model<S, T>(smem, a.model);
   const Grp<G> g = make_group<G>();
@@ -125,7 +140,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_r
   }
 }
 
-template <class S, typename T, int G> __global__ void __launch_bounds__(512) k_contacts(KmArgs a) {
+template <class S, typename T, int G> __global__ void __launch_bounds__(max_threads<S, T>()) k_contacts(KmArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Model<S, T>& m = stage_model<S, T>(smem, a.model);
   const Grp<G> g = make_group<G>();
@@ -161,11 +176,8 @@ template <class S, typename T> struct Launch {
     return cudaGetLastError();
   }
   static cudaError_t dispatch(int which, const KmArgs& a) {
-    switch (a.G) {
-      case 8: return run<8>(which, a);
-      case 16: return run<16>(which, a);
-      case 32: return run<32>(which, a);
-    }
+    if (a.G == 32) return run<32>(which, a);
+    if constexpr (D::NV <= 16) { if (a.G == 16) return run<16>(which, a); }
     return cudaErrorInvalidValue;
   }
   static cudaError_t step(const KmArgs& a) { return dispatch(0, a); }
@@ -180,11 +192,8 @@ template <class S, typename T> struct Launch {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, sm);
   }
   static cudaError_t prepare(int G, int epb, int* ctas) {
-    switch (G) {
-      case 8: return prep<8>(epb, ctas);
-      case 16: return prep<16>(epb, ctas);
-      case 32: return prep<32>(epb, ctas);
-    }
+    if (G == 32) return prep<32>(epb, ctas);
+    if constexpr (D::NV <= 16) { if (G == 16) return prep<16>(epb, ctas); }
     return cudaErrorInvalidValue;
   }
   static int fill(const km_model* fm, const km_task* tk, void* dst, std::string& err) {
@@ -194,7 +203,7 @@ template <class S, typename T> struct Launch {
     KmVtable v;
     v.model_bytes = sizeof(Model<S, T>); v.env_bytes = env_smem<S, T>(); v.scalar_bytes = sizeof(T);
     v.nq = D::NQ; v.nv = D::NV; v.nu = D::NU; v.nmocap = D::NMOCAP; v.obs_dim = D::OBS;
-    v.state_dim = D::NQ + 2 * D::NV + D::NU + 7 * D::NMOCAP + 1; v.maxcon = D::MAXCON; v.nlanes_min = 8;
+    v.state_dim = D::NQ + 2 * D::NV + D::NU + 7 * D::NMOCAP + 1; v.maxcon = D::MAXCON; v.nlanes_min = D::NV <= 16 ? 16 : 32; v.max_threads = max_threads<S, T>();
     v.fill = &fill; v.step = &step; v.reset = &reset; v.contacts = &contacts; v.prepare = &prepare;
     return v;
   }

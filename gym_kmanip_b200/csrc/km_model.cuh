@@ -40,12 +40,26 @@ template <class S> struct Dim {
   static_assert(NV <= 32, "dof support masks are 32-bit");
 };
 
+// Diagonal block (kinematic chain, or the cube) of dof j in the mass matrix: [blk_begin, blk_end).  Known at compile
+// time from the scene header, so the factorisation can skip structurally zero blocks without run-time tests.
+template <class S> constexpr int dof_root(int j) {
+  while (S::dof_parent[j] >= 0) j = S::dof_parent[j];
+  return j;
+}
+template <class S> constexpr int blk_end(int j) {
+  if (j >= S::NVA) return S::NVA + 6;
+  int e = j + 1;
+  while (e < S::NVA && dof_root<S>(e) == dof_root<S>(j)) e++;
+  return e;
+}
+
 // -------------------------------------------------------------------------------------------- model
 template <class S, typename T> struct Model {
   typedef Dim<S> D;
   // links
   int parent[D::NVA], jtype[D::NVA], sub_end[D::NVA];
   unsigned ancmask[D::NVA];                       // bit j set: dof j is l or an ancestor of l
+  unsigned short pair_ij[D::NV * (D::NV + 1) / 2]; // lower-triangle work list: i << 8 | j
   int nlevel, level_adr[D::MAXLEVEL + 1], level_link[D::NVA];
   T lpos[D::NVA][3], lquat[D::NVA][4];            // pose in the parent link, or in the world when parent < 0
   T mass[D::NVA], ipos[D::NVA][3], inertia[D::NVA][3];
@@ -53,8 +67,8 @@ template <class S, typename T> struct Model {
   T range[D::NVA][2], lim_invw[D::NVA], lim_solref[D::NVA][2], lim_solimp[D::NVA][7];
   T kp[D::NVA], ctrl_lo[D::NVA], ctrl_hi[D::NVA], frc_lo[D::NVA], frc_hi[D::NVA];
   // friction-loss rows (constant: pos = 0)
-  int fric_dof[D::NFRIC];
-  T fr_loss[D::NFRIC], fr_R[D::NFRIC], fr_D[D::NFRIC], fr_B[D::NFRIC];
+  int fric_dof[D::NFRIC], dof_fric[D::NV];         // row <-> dof of the friction-loss rows (-1: none)
+  T fr_loss[D::NFRIC], fr_R[D::NFRIC], fr_Rf[D::NFRIC], fr_D[D::NFRIC], fr_B[D::NFRIC];   // fr_Rf = R * loss
   // finger pads (spheres) vs cube
   int pad_link[D::NPAD], pad_geom[D::NPAD], pad_arm[D::NPAD];
   T pad_pos[D::NPAD][3], pad_rad[D::NPAD], pad_mu[D::NPAD][3], pad_solref[D::NPAD][2], pad_solimp[D::NPAD][7];
@@ -82,40 +96,54 @@ template <class S, typename T> struct Env {
   // persistent state (what km_get_state / km_set_state expose)
   T qpos[D::NQ], qvel[D::NV], ctrl[D::NU], warm[D::NV], mocap[D::NMOCAP * 7], time;
   int step, episode;
-  // position stage
-  T xpos[D::NVA][3], xquat[D::NVA][4], xmat[D::NVA][9], xipos[D::NVA][3];
+  // position stage: link frames, cube rotation, mass matrix (articulated block; the cube block is a constant diagonal)
+  T xpos[D::NVA][3], xquat[D::NVA][4], xmat[D::NVA][9];
   T cmat[9], com[3];
-  T cdof[D::NVA][6], cinert[D::NVA][10];
-  T M[D::NVA][D::NVA];                            // articulated block (cube block is constant diagonal)
-  T Lm[D::NVA][D::NVA + 1], Lmd[D::NVA];          // its Cholesky factor
+  T M[D::NVA][D::NVA];
   T actlen[D::NU];
   // collision
   int sl_on[D::NSLOT];
   T sl_dist[D::NSLOT], sl_pos[D::NSLOT][3], sl_frame[D::NSLOT][9];
   int ncon, con_slot[D::MAXCON];
   unsigned con_sup[D::MAXCON];                    // dof support of the contact's Jacobian rows
-  T con_mu[D::MAXCON][3], con_D[D::MAXCON], con_W[D::MAXCON][3];
-  T Jc[D::MAXCON][4][D::NV];                      // base rows: normal, tangent1, tangent2, torsion
-  T cb[D::MAXCON][4];                             // base-row products / base-row forces
-  // constraint rows
-  int nefc, nlim;
+  T con_mu[D::MAXCON][3], con_D[D::MAXCON], con_B[D::MAXCON], con_Kip[D::MAXCON], con_W[D::MAXCON][3];
+  // contact Jacobian base rows (normal, tangent1, tangent2, torsion): cube columns of every contact,
+  // articulated columns of the finger-pad slots only (the table touches nothing but the cube)
+  T Jq[D::MAXCON][4][6], Ja[D::NPAD][4][D::NVA];
+  T cb[D::MAXCON][4];                             // base-row products / base-row forces / Hessian weights
+  // constraint rows: friction loss (constant, first NFRIC rows), active joint limits, 6 pyramid rows per contact
+  int nefc, nlim, coupled;                        // coupled: a finger pad touches the cube (arm and cube blocks interact)
+  int dof_lim[D::NVA];                            // active limit row of each joint, or -1
   int efc_desc[D::MAXEFC];
-  T efc_D[D::MAXEFC], efc_R[D::MAXEFC], efc_B[D::MAXEFC], efc_Kip[D::MAXEFC], efc_aref[D::MAXEFC], efc_floss[D::MAXEFC];
-  T efc_jar[D::MAXEFC], efc_jv[D::MAXEFC], efc_force[D::MAXEFC];
-  int efc_state[D::MAXEFC];
-  // velocity stage
-  T cvel[D::NVA][6], cdof_dot[D::NVA][6], cfrc[D::NVA][6], bias[D::NV];
-  // acceleration stage
-  T qfrc_smooth[D::NV], qacc_smooth[D::NV], qacc[D::NV];
-  // solver / IK scratch
-  T Ma[D::NV], grad[D::NV], Mgrad[D::NV], search[D::NV], Mv[D::NV], qfc[D::NV];
-  T H[D::NV][D::HS], Hd[D::NV];
-  T ik_J[6][D::MAXMASK], ik_r[D::NRES], ik_rn[D::NRES], ik_x[D::MAXMASK], ik_xn[D::MAXMASK], ik_lo[D::MAXMASK],
-      ik_hi[D::MAXMASK], ik_qprev[D::MAXMASK], ik_goal[2][7];
-  int ik_active[D::MAXMASK];
+  T efc_D[D::MAXEFC], efc_aref[D::MAXEFC], efc_jv[D::MAXEFC];
+  T lim_B[D::NVA], lim_Kip[D::NVA];
+  T bias[D::NV], qfrc_smooth[D::NV], qacc_smooth[D::NV], qacc[D::NV];
+  T ik_goal[2][7];
   T obs[D::OBS];
-  // diagnostics of the last sub-step
-  int solver_niter, ls_evals;
+  int solver_niter, ls_evals;                     // diagnostics of the last sub-step
+  // Scratch that is live in disjoint phases shares storage:
+  //   a: position/velocity stage (step1)   b: IK between step1 and step2 (also uses c.H, c.Hd, c.Mgrad)
+  //   c: Newton solver (step2); its first three arrays are at least as large as b, which may only overlay those
+  struct StageA {
+    T cdof[D::NVA][6], cinert[D::NVA][10], cvel[D::NVA][6], cdof_dot[D::NVA][6], cfrc[D::NVA][6];
+  };
+  struct StageB {
+    T ik_J[6][D::MAXMASK], ik_r[D::NRES], ik_rn[D::NRES], ik_x[D::MAXMASK], ik_xn[D::MAXMASK], ik_lo[D::MAXMASK],
+        ik_hi[D::MAXMASK], ik_qprev[D::MAXMASK];
+    int ik_active[D::MAXMASK];
+  };
+  struct StageC {
+    T efc_jar[D::MAXEFC], efc_force[D::MAXEFC];
+    int efc_state[D::MAXEFC];
+    T Ma[D::NV], grad[D::NV], Mgrad[D::NV], search[D::NV], Mv[D::NV], qfc[D::NV], hdiag[D::NV];
+    T H[D::NV][D::HS], Hd[D::NV];
+  };
+  union {
+    StageA a;
+    StageB b;
+    StageC c;
+  };
+  static_assert(sizeof(StageB) <= offsetof(StageC, Ma), "IK scratch may only overlay the solver's row arrays");
 };
 
 // efc row descriptor: type | id << 2 | k << 10 | neg << 12   (id = dof for friction/limit rows, contact for contact rows;

@@ -47,9 +47,7 @@ KM_TPL KM_FN void kinematics(KM_ARGS) {
       if (m.jtype[l] == JT_SLIDE) { pos[0] += mat[2] * th; pos[1] += mat[5] * th; pos[2] += mat[8] * th; }
       for (int i = 0; i < 4; i++) e.xquat[l][i] = q[i];
       for (int i = 0; i < 9; i++) e.xmat[l][i] = mat[i];
-      T ip[3];
-      mulv3(ip, mat, m.ipos[l]);
-      for (int i = 0; i < 3; i++) { e.xpos[l][i] = pos[i]; e.xipos[l][i] = pos[i] + ip[i]; }
+      for (int i = 0; i < 3; i++) e.xpos[l][i] = pos[i];
     }
     g.sync();
   }
@@ -60,38 +58,40 @@ KM_TPL KM_FN void com_crb(KM_ARGS) {
   typedef Dim<S> D;
   KM_FOR(k, 3) {
     T s = 0;
-    for (int l = 0; l < D::NVA; l++) s += m.mass[l] * e.xipos[l][k];
+    for (int l = 0; l < D::NVA; l++)
+      s += m.mass[l] * (e.xpos[l][k] + e.xmat[l][3 * k] * m.ipos[l][0] + e.xmat[l][3 * k + 1] * m.ipos[l][1] + e.xmat[l][3 * k + 2] * m.ipos[l][2]);
     e.com[k] = s * m.total_mass_inv;
   }
   g.sync();
   KM_FOR(l, D::NVA) {
-    T off[3] = {e.xipos[l][0] - e.com[0], e.xipos[l][1] - e.com[1], e.xipos[l][2] - e.com[2]};
-    T ci[10];
+    T off[3], ci[10];
+    mulv3(off, e.xmat[l], m.ipos[l]);
+    for (int k = 0; k < 3; k++) off[k] += e.xpos[l][k] - e.com[k];
     inert_com(ci, m.inertia[l], e.xmat[l], off, m.mass[l]);
-    for (int i = 0; i < 10; i++) e.cinert[l][i] = ci[i];
+    for (int i = 0; i < 10; i++) e.a.cinert[l][i] = ci[i];
     const T ax[3] = {e.xmat[l][2], e.xmat[l][5], e.xmat[l][8]};
     if (m.jtype[l] == JT_SLIDE) {
-      e.cdof[l][0] = 0; e.cdof[l][1] = 0; e.cdof[l][2] = 0;
-      e.cdof[l][3] = ax[0]; e.cdof[l][4] = ax[1]; e.cdof[l][5] = ax[2];
+      e.a.cdof[l][0] = 0; e.a.cdof[l][1] = 0; e.a.cdof[l][2] = 0;
+      e.a.cdof[l][3] = ax[0]; e.a.cdof[l][4] = ax[1]; e.a.cdof[l][5] = ax[2];
     } else {
       T o[3] = {e.com[0] - e.xpos[l][0], e.com[1] - e.xpos[l][1], e.com[2] - e.xpos[l][2]}, c[3];
       cross3(c, ax, o);
-      e.cdof[l][0] = ax[0]; e.cdof[l][1] = ax[1]; e.cdof[l][2] = ax[2];
-      e.cdof[l][3] = c[0]; e.cdof[l][4] = c[1]; e.cdof[l][5] = c[2];
+      e.a.cdof[l][0] = ax[0]; e.a.cdof[l][1] = ax[1]; e.a.cdof[l][2] = ax[2];
+      e.a.cdof[l][3] = c[0]; e.a.cdof[l][4] = c[1]; e.a.cdof[l][5] = c[2];
     }
   }
   g.sync();
   // composite inertia of link i's subtree times its own motion axis, projected on the ancestors' axes
   KM_FOR(i, D::NVA) {
     T crb[10];
-    for (int k = 0; k < 10; k++) crb[k] = e.cinert[i][k];
+    for (int k = 0; k < 10; k++) crb[k] = e.a.cinert[i][k];
     for (int c = i + 1; c < m.sub_end[i]; c++)
-      for (int k = 0; k < 10; k++) crb[k] += e.cinert[c][k];
+      for (int k = 0; k < 10; k++) crb[k] += e.a.cinert[c][k];
     T buf[6];
-    mul_inert_vec(buf, crb, e.cdof[i]);
+    mul_inert_vec(buf, crb, e.a.cdof[i]);
     for (int j = i; j >= 0; j = m.parent[j]) {
       T s = 0;
-      for (int k = 0; k < 6; k++) s += e.cdof[j][k] * buf[k];
+      for (int k = 0; k < 6; k++) s += e.a.cdof[j][k] * buf[k];
       e.M[i][j] = s; e.M[j][i] = s;
     }
   }
@@ -138,12 +138,109 @@ KM_TPL KM_FN void chol_solve(const T* A, const T* diag, T* x, int n, int ld, con
   }
 }
 
-KM_TPL KM_FN void factor_m(KM_ARGS) {
+// contact Jacobian base row b of contact c at dof col (col must lie in the contact's support)
+template <class S, typename T> KM_HD T jc(const Env<S, T>& e, int c, int b, int col) {
   typedef Dim<S> D;
-  KM_FOR(i, D::NVA)
-    for (int j = 0; j <= i; j++) e.Lm[i][j] = e.M[i][j];
+  return col >= D::NVA ? e.Jq[c][b][col - D::NVA] : e.Ja[e.con_slot[c] < D::NPAD ? e.con_slot[c] : 0][b][col];
+}
+
+// dst = A^{-1} rhs for the SPD matrix whose lower triangle has been assembled in e.c.H.
+// Device: lane i keeps row i of the Cholesky factor in registers; pivots and multipliers travel by warp
+// shuffles, so the factorisation and both triangular solves need no shared-memory round trips and no barriers
+// except one transpose through e.c.H.  DENSE = false skips the blocks that are structurally zero at compile time
+// (other kinematic chains; the cube while no finger pad touches it).  The body is branch-free on purpose: ptxas
+// wraps every shuffle that follows a potentially divergent branch in a WARPSYNC.COLLECTIVE sequence.
+// Host build (tests only): plain dense Cholesky.
+template <class S, typename T, int G, bool DENSE> KM_FN void solve_spd(KM_ARGS, const T* rhs, T* dst) {
+  typedef Dim<S> D;
+  typedef Num<T> N;
+  constexpr int NV = D::NV;
+#if defined(__CUDA_ARCH__)
+  static_assert(G >= NV, "one lane per dof row");
   g.sync();
-  chol_factor<S, T, G>(&e.Lm[0][0], e.Lmd, D::NVA, D::NVA + 1, g);
+  const int i = g.lane, ic = i < NV ? i : NV - 1;   // surplus lanes shadow the last row
+  T row[NV];
+  sfor<0, NV>([&](auto J) { row[decltype(J)::value] = e.c.H[ic][decltype(J)::value]; });
+  T dinv = 1;
+  sfor<0, NV>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const T ajj = g.shfl(row[j], j);
+    const T inv = N::rsqrt(tmax(ajj, N::minval()));
+    const T lij = row[j] * inv;
+    row[j] = lij;
+    dinv = ic == j ? inv : dinv;
+    constexpr int KE = DENSE ? NV : blk_end<S>(j);
+    sfor<j + 1, KE>([&](auto K) {
+      constexpr int k = decltype(K)::value;
+      row[k] -= lij * g.shfl(lij, k);
+    });
+  });
+  // forward substitution, row-oriented
+  T acc = rhs[ic], y = 0;
+  sfor<0, NV>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const T yj = g.shfl(acc * dinv, j);
+    y = ic == j ? yj : y;
+    acc -= (ic > j ? row[j] : T(0)) * yj;
+  });
+  // transpose the factor through shared memory: lane i then holds column i (entries below the diagonal)
+  sfor<0, NV>([&](auto J) { e.c.H[ic][decltype(J)::value] = row[decltype(J)::value]; });
+  g.sync();
+  T col[NV];
+  sfor<0, NV>([&](auto K) {
+    constexpr int k = decltype(K)::value;
+    const T v = e.c.H[k][ic];
+    col[k] = k > ic ? v : T(0);
+  });
+  T acc2 = y, x = 0;
+  sfor_rev<NV>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const T xj = g.shfl(acc2 * dinv, j);
+    x = ic == j ? xj : x;
+    acc2 -= col[j] * xj;
+  });
+  dst[ic] = x;
+  g.sync();
+#else
+  if (dst != rhs)
+    for (int i = 0; i < NV; i++) dst[i] = rhs[i];
+  chol_factor<S, T, G>(&e.c.H[0][0], e.c.Hd, NV, D::HS, g);
+  chol_solve<S, T, G>(&e.c.H[0][0], e.c.Hd, dst, NV, D::HS, g);
+#endif
+}
+
+// one lower-triangle entry (i >= j) of J^T diag(D_active) J restricted to the contacts
+KM_TPL KM_HD T hess_contacts(const Env<S, T>& e, int i, int j) {
+  T h = 0;
+  for (int c = 0; c < e.ncon; c++) {
+    const unsigned sup = e.con_sup[c];
+    if (((sup >> i) & 1u) && ((sup >> j) & 1u)) {
+      const T ni = jc<S, T>(e, c, 0, i), nj = jc<S, T>(e, c, 0, j);
+      T acc = e.cb[c][0] * ni * nj;
+      for (int k = 1; k < 4; k++) {
+        const T ki = jc<S, T>(e, c, k, i), kj = jc<S, T>(e, c, k, j);
+        acc += e.cb[c][k] * (ni * kj + ki * nj) + e.con_W[c][k - 1] * ki * kj;
+      }
+      h += acc;
+    }
+  }
+  return h;
+}
+
+// lower triangle of e.c.H = M + diag(hdiag) [+ contact terms when with_contacts]
+KM_TPL KM_HD void assemble_h(KM_ARGS, bool with_contacts) {
+  typedef Dim<S> D;
+  KM_FOR(w, D::NV * (D::NV + 1) / 2) {
+    const int ij = m.pair_ij[w], i = ij >> 8, j = ij & 255;
+    T h;
+    if (i < D::NVA) h = e.M[i][j];
+    else h = i == j ? (i - D::NVA < 3 ? m.cube_mass : m.cube_inertia[i - D::NVA - 3]) : T(0);
+    if (i == j) h += e.c.hdiag[i];
+    // contact terms: the cube block always; arm rows only while a finger pad touches the cube
+    if (with_contacts && (e.coupled || j >= D::NVA)) h += hess_contacts<S, T, G>(e, i, j);
+    e.c.H[i][j] = h;
+  }
+  g.sync();
 }
 
 // mj_collision on the primitive pairs of the completed model: finger-pad spheres vs the cube box, then the
@@ -217,6 +314,7 @@ KM_TPL KM_FN void collision(KM_ARGS) {
       e.con_slot[n++] = s;
     }
     e.ncon = n;
+    e.coupled = n > 0 && e.con_slot[0] < D::NPAD;
   }
   g.sync();
 }
@@ -235,9 +333,7 @@ template <typename T> KM_HD T impedance(const T* solimp, T pos, T* omi) {
   if (x == T(0)) { *omi = omin; return dmin; }
   T y;
   if (power == T(1)) y = x;
-  else if (power == T(2)) y = x <= mid ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
-  else if (x <= mid) y = N::pow(x, power) / N::pow(mid, power - T(1));
-  else y = T(1) - N::pow(T(1) - x, power) / N::pow(T(1) - mid, power - T(1));
+  else y = x <= mid ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);   // power == 2 (km_fill.h checks)
   *omi = omin - y * (dmax - dmin);
   return dmin + y * (dmax - dmin);
 }
@@ -252,6 +348,7 @@ KM_TPL KM_FN void make_constraint(KM_ARGS) {
     int r = D::NFRIC;
     for (int j = 0; j < D::NVA; j++) {
       const T q = e.qpos[j];
+      e.dof_lim[j] = -1;
       for (int side = 0; side < 2; side++) {
         const T dist = side == 0 ? q - m.range[j][0] : m.range[j][1] - q;
         if (dist < T(0)) {
@@ -260,9 +357,10 @@ KM_TPL KM_FN void make_constraint(KM_ARGS) {
           const T R = tmax(N::minval(), omi * m.lim_invw[j] / imp);
           const T tc = tmax(m.lim_solref[j][0], T(2) * m.h), dr = m.lim_solref[j][1], dmax = m.lim_solimp[j][1];
           e.efc_desc[r] = efc_pack(EFC_LIMIT, j, 0, side);
-          e.efc_R[r] = R; e.efc_D[r] = T(1) / R; e.efc_floss[r] = 0;
-          e.efc_B[r] = T(2) / (dmax * tc);
-          e.efc_Kip[r] = (T(1) / (dmax * dmax * tc * tc * dr * dr)) * imp * dist;
+          e.dof_lim[j] = r;
+          e.efc_D[r] = T(1) / R;
+          e.lim_B[r - D::NFRIC] = T(2) / (dmax * tc);
+          e.lim_Kip[r - D::NFRIC] = (T(1) / (dmax * dmax * tc * tc * dr * dr)) * imp * dist;
           r++;
         }
       }
@@ -287,13 +385,13 @@ KM_TPL KM_FN void make_constraint(KM_ARGS) {
     const T R = T(2) * mu * mu * R1, Dc = T(1) / R;
     const T tc = tmax(solref[0], T(2) * m.h), dr = solref[1], dmax = solimp[1];
     const T B = T(2) / (dmax * tc), Kip = (T(1) / (dmax * dmax * tc * tc * dr * dr)) * imp * dist;
-    e.con_D[c] = Dc;
+    e.con_D[c] = Dc; e.con_B[c] = B; e.con_Kip[c] = Kip;
     for (int k = 0; k < 3; k++) e.con_mu[c][k] = mu3[k];
     e.con_sup[c] = (s < D::NPAD ? m.ancmask[m.pad_link[s]] : 0u) | (63u << D::NVA);
     for (int k = 0; k < 6; k++) {
       const int r = base + 6 * c + k;
       e.efc_desc[r] = efc_pack(EFC_CONTACT, c, 1 + k / 2, k & 1);
-      e.efc_R[r] = R; e.efc_D[r] = Dc; e.efc_B[r] = B; e.efc_Kip[r] = Kip; e.efc_floss[r] = 0;
+      e.efc_D[r] = Dc;
     }
   }
   // contact Jacobian base rows, J = J(cube) - J(pad link), one (contact, dof) per work item
@@ -324,10 +422,12 @@ KM_TPL KM_FN void make_constraint(KM_ARGS) {
       }
     } else on = false;
     if (on) {
-      e.Jc[c][0][col] = dot3(f, jp);
-      e.Jc[c][1][col] = dot3(f + 3, jp);
-      e.Jc[c][2][col] = dot3(f + 6, jp);
-      e.Jc[c][3][col] = dot3(f, jr);
+      T* dst = col >= D::NVA ? &e.Jq[c][0][col - D::NVA] : &e.Ja[s][0][col];
+      const int st = col >= D::NVA ? 6 : D::NVA;   // stride between base rows
+      dst[0] = dot3(f, jp);
+      dst[st] = dot3(f + 3, jp);
+      dst[2 * st] = dot3(f + 6, jp);
+      dst[3 * st] = dot3(f, jr);
     }
   }
   g.sync();
@@ -338,10 +438,11 @@ KM_TPL KM_FN void mul_J(KM_ARGS, const T* x, T* out) {
   typedef Dim<S> D;
   KM_FOR(w, e.ncon * 4) {
     const int c = w >> 2, b = w & 3;
-    const unsigned sup = e.con_sup[c];
     T s = 0;
-    for (int j = 0; j < D::NV; j++)
-      if ((sup >> j) & 1u) s += e.Jc[c][b][j] * x[j];
+    for (int k = 0; k < 6; k++) s += e.Jq[c][b][k] * x[D::NVA + k];
+    const int sl = e.con_slot[c];
+    if (sl < D::NPAD)
+      for (int j = m.pad_link[sl]; j >= 0; j = m.parent[j]) s += e.Ja[sl][b][j] * x[j];
     e.cb[c][b] = s;
   }
   g.sync();
@@ -357,12 +458,12 @@ KM_TPL KM_FN void mul_J(KM_ARGS, const T* x, T* out) {
   g.sync();
 }
 
-// e.qfc = J^T efc_force
+// e.c.qfc = J^T efc_force
 KM_TPL KM_FN void mul_JT_force(KM_ARGS) {
   typedef Dim<S> D;
   const int base = D::NFRIC + e.nlim;
   KM_FOR(c, e.ncon) {
-    const T* f = e.efc_force + base + 6 * c;
+    const T* f = e.c.efc_force + base + 6 * c;
     e.cb[c][0] = f[0] + f[1] + f[2] + f[3] + f[4] + f[5];
     e.cb[c][1] = e.con_mu[c][0] * (f[0] - f[1]);
     e.cb[c][2] = e.con_mu[c][1] * (f[2] - f[3]);
@@ -371,14 +472,14 @@ KM_TPL KM_FN void mul_JT_force(KM_ARGS) {
   g.sync();
   KM_FOR(i, D::NV) {
     T s = 0;
-    for (int r = 0; r < base; r++) {
-      const int d = e.efc_desc[r];
-      if (efc_id(d) == i) s += efc_neg(d) ? -e.efc_force[r] : e.efc_force[r];
-    }
+    const int fr = m.dof_fric[i], lr = i < D::NVA ? e.dof_lim[i] : -1;
+    if (fr >= 0) s += e.c.efc_force[fr];
+    if (lr >= 0) s += efc_neg(e.efc_desc[lr]) ? -e.c.efc_force[lr] : e.c.efc_force[lr];
     for (int c = 0; c < e.ncon; c++)
       if ((e.con_sup[c] >> i) & 1u)
-        s += e.Jc[c][0][i] * e.cb[c][0] + e.Jc[c][1][i] * e.cb[c][1] + e.Jc[c][2][i] * e.cb[c][2] + e.Jc[c][3][i] * e.cb[c][3];
-    e.qfc[i] = s;
+        s += jc<S, T>(e, c, 0, i) * e.cb[c][0] + jc<S, T>(e, c, 1, i) * e.cb[c][1] + jc<S, T>(e, c, 2, i) * e.cb[c][2] +
+             jc<S, T>(e, c, 3, i) * e.cb[c][3];
+    e.c.qfc[i] = s;
   }
   g.sync();
 }
@@ -401,11 +502,10 @@ KM_TPL KM_FN void mul_M(KM_ARGS, const T* x, T* out) {
   g.sync();
 }
 
-KM_TPL KM_FN void fwd_position(KM_ARGS) {
+KM_TPL KM_HD void fwd_position(KM_ARGS) {
   typedef Dim<S> D;
   kinematics<S, T, G>(e, m, g);
   com_crb<S, T, G>(e, m, g);
-  factor_m<S, T, G>(e, m, g);
   collision<S, T, G>(e, m, g);
   make_constraint<S, T, G>(e, m, g);
   KM_FOR(i, D::NU) e.actlen[i] = e.qpos[i];   // mj_transmission: joint transmissions, gear 1
@@ -420,29 +520,29 @@ KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
     T v[6] = {0, 0, 0, 0, 0, 0};
     for (int j = l; j >= 0; j = m.parent[j]) {
       const T qv = e.qvel[j];
-      for (int k = 0; k < 6; k++) v[k] += e.cdof[j][k] * qv;
+      for (int k = 0; k < 6; k++) v[k] += e.a.cdof[j][k] * qv;
     }
-    for (int k = 0; k < 6; k++) e.cvel[l][k] = v[k];
+    for (int k = 0; k < 6; k++) e.a.cvel[l][k] = v[k];
   }
   g.sync();
   KM_FOR(l, D::NVA) {
     const int p = m.parent[l];
     T r[6] = {0, 0, 0, 0, 0, 0};
-    if (p >= 0) cross_motion(r, e.cvel[p], e.cdof[l]);
-    for (int k = 0; k < 6; k++) e.cdof_dot[l][k] = r[k];
+    if (p >= 0) cross_motion(r, e.a.cvel[p], e.a.cdof[l]);
+    for (int k = 0; k < 6; k++) e.a.cdof_dot[l][k] = r[k];
   }
   g.sync();
   KM_FOR(l, D::NVA) {
     T a[6] = {0, 0, 0, -m.grav[0], -m.grav[1], -m.grav[2]};
     for (int j = l; j >= 0; j = m.parent[j]) {
       const T qv = e.qvel[j];
-      for (int k = 0; k < 6; k++) a[k] += e.cdof_dot[j][k] * qv;
+      for (int k = 0; k < 6; k++) a[k] += e.a.cdof_dot[j][k] * qv;
     }
     T f[6], t1[6], t2[6];
-    mul_inert_vec(f, e.cinert[l], a);
-    mul_inert_vec(t1, e.cinert[l], e.cvel[l]);
-    cross_force(t2, e.cvel[l], t1);
-    for (int k = 0; k < 6; k++) e.cfrc[l][k] = f[k] + t2[k];
+    mul_inert_vec(f, e.a.cinert[l], a);
+    mul_inert_vec(t1, e.a.cinert[l], e.a.cvel[l]);
+    cross_force(t2, e.a.cvel[l], t1);
+    for (int k = 0; k < 6; k++) e.a.cfrc[l][k] = f[k] + t2[k];
   }
   g.sync();
   KM_FOR(i, D::NV) {
@@ -450,8 +550,8 @@ KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
     if (i < D::NVA) {
       T f[6] = {0, 0, 0, 0, 0, 0};
       for (int c = i; c < m.sub_end[i]; c++)
-        for (int k = 0; k < 6; k++) f[k] += e.cfrc[c][k];
-      for (int k = 0; k < 6; k++) s += e.cdof[i][k] * f[k];
+        for (int k = 0; k < 6; k++) f[k] += e.a.cfrc[c][k];
+      for (int k = 0; k < 6; k++) s += e.a.cdof[i][k] * f[k];
     } else {
       // free cube with its COM at the body origin: bias = [-m g ; w x (I w)] (w in the body frame)
       const int k = i - D::NVA;
@@ -468,7 +568,14 @@ KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
   }
   // reference acceleration of every row: aref = -B (J qvel) - K imp pos
   mul_J<S, T, G>(e, m, g, e.qvel, e.efc_jv);
-  KM_FOR(r, e.nefc) e.efc_aref[r] = -e.efc_B[r] * e.efc_jv[r] - e.efc_Kip[r];
+  const int base = D::NFRIC + e.nlim;
+  KM_FOR(r, e.nefc) {
+    T B, Kip;
+    if (r < D::NFRIC) { B = m.fr_B[r]; Kip = 0; }
+    else if (r < base) { B = e.lim_B[r - D::NFRIC]; Kip = e.lim_Kip[r - D::NFRIC]; }
+    else { const int c = (r - base) / 6; B = e.con_B[c]; Kip = e.con_Kip[c]; }
+    e.efc_aref[r] = -B * e.efc_jv[r] - Kip;
+  }
   g.sync();
 }
 
@@ -484,17 +591,17 @@ KM_TPL KM_FN void fwd_actuation_acceleration(KM_ARGS) {
     }
     const T s = f - e.bias[i];
     e.qfrc_smooth[i] = s;
-    e.qacc_smooth[i] = i < D::NVA ? s : s / (i - D::NVA < 3 ? m.cube_mass : m.cube_inertia[i - D::NVA - 3]);
+    e.c.hdiag[i] = 0;
   }
   g.sync();
-  chol_solve<S, T, G>(&e.Lm[0][0], e.Lmd, e.qacc_smooth, D::NVA, D::NVA + 1, g);
+  assemble_h<S, T, G>(e, m, g, false);
+  solve_spd<S, T, G, false>(e, m, g, e.qfrc_smooth, e.qacc_smooth);
 }
 
 // ---- Newton solver (mj_solNewton on the primal problem)
 // constraint cost pieces of one row at residual x: returns the cost, sets state and force
-template <typename T> KM_HD T row_cost(int type, T x, T Dr, T R, T floss, int* state, T* force) {
-  if (type == EFC_FRICTION) {
-    const T rf = R * floss;
+template <typename T> KM_HD T row_cost(bool friction, T x, T Dr, T rf, T floss, int* state, T* force) {
+  if (friction) {
     if (x <= -rf) { *state = ST_LINEARNEG; *force = floss; return -floss * (T(0.5) * rf + x); }
     if (x >= rf) { *state = ST_LINEARPOS; *force = -floss; return -floss * (T(0.5) * rf - x); }
     *state = ST_QUADRATIC; *force = -Dr * x; return T(0.5) * Dr * x * x;
@@ -507,14 +614,15 @@ template <typename T> KM_HD T row_cost(int type, T x, T Dr, T R, T floss, int* s
 KM_TPL KM_FN T total_cost(KM_ARGS, const T* a) {
   typedef Dim<S> D;
   mul_J<S, T, G>(e, m, g, a, e.efc_jv);
-  mul_M<S, T, G>(e, m, g, a, e.Mv);
+  mul_M<S, T, G>(e, m, g, a, e.c.Mv);
   T c = 0;
   KM_FOR(r, e.nefc) {
     int st; T f;
-    c += row_cost(efc_type(e.efc_desc[r]), e.efc_jv[r] - e.efc_aref[r], e.efc_D[r], e.efc_R[r], e.efc_floss[r], &st, &f);
+    const bool fr = r < D::NFRIC;
+    c += row_cost(fr, e.efc_jv[r] - e.efc_aref[r], e.efc_D[r], fr ? m.fr_Rf[r] : T(0), fr ? m.fr_loss[r] : T(0), &st, &f);
   }
   T gs = 0;
-  KM_FOR(i, D::NV) gs += (e.Mv[i] - e.qfrc_smooth[i]) * (a[i] - e.qacc_smooth[i]);
+  KM_FOR(i, D::NV) gs += (e.c.Mv[i] - e.qfrc_smooth[i]) * (a[i] - e.qacc_smooth[i]);
   c = g.sum(c + T(0.5) * gs);
   g.sync();
   return c;
@@ -526,15 +634,16 @@ KM_TPL KM_FN T sol_update(KM_ARGS, T* gauss) {
   T c = 0;
   KM_FOR(r, e.nefc) {
     int st; T f;
-    c += row_cost(efc_type(e.efc_desc[r]), e.efc_jar[r], e.efc_D[r], e.efc_R[r], e.efc_floss[r], &st, &f);
-    e.efc_state[r] = st; e.efc_force[r] = f;
+    const bool fr = r < D::NFRIC;
+    c += row_cost(fr, e.c.efc_jar[r], e.efc_D[r], fr ? m.fr_Rf[r] : T(0), fr ? m.fr_loss[r] : T(0), &st, &f);
+    e.c.efc_state[r] = st; e.c.efc_force[r] = f;
   }
   g.sync();
   mul_JT_force<S, T, G>(e, m, g);
   T gs = 0;
   KM_FOR(i, D::NV) {
-    gs += (e.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
-    e.grad[i] = e.Ma[i] - e.qfrc_smooth[i] - e.qfc[i];
+    gs += (e.c.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
+    e.c.grad[i] = e.c.Ma[i] - e.qfrc_smooth[i] - e.c.qfc[i];
   }
   c = g.sum(c);
   gs = T(0.5) * g.sum(gs);
@@ -549,7 +658,7 @@ KM_TPL KM_FN void sol_hessian_dir(KM_ARGS) {
   const int base = D::NFRIC + e.nlim;
   // per-contact weights of the base rows: W = sum_active D w w^T, w = e0 +- mu_k e_k  (arrow-head 4x4)
   KM_FOR(c, e.ncon) {
-    const int* st = e.efc_state + base + 6 * c;
+    const int* st = e.c.efc_state + base + 6 * c;
     const T Dc = e.con_D[c];
     T n = 0;
     for (int k = 0; k < 3; k++) {
@@ -559,48 +668,29 @@ KM_TPL KM_FN void sol_hessian_dir(KM_ARGS) {
       e.cb[c][1 + k] = Dc * mu * (p - q);        // W[0][k]
       e.con_W[c][k] = Dc * mu * mu * (p + q);    // W[k][k]
     }
-    e.cb[c][0] = Dc * n;                                // W[0][0]
+    e.cb[c][0] = Dc * n;                         // W[0][0]
+  }
+  // diagonal contributions of the friction-loss and limit rows (each touches one dof)
+  KM_FOR(i, D::NV) {
+    T d = 0;
+    const int fr = m.dof_fric[i], lr = i < D::NVA ? e.dof_lim[i] : -1;
+    if (fr >= 0 && e.c.efc_state[fr] == ST_QUADRATIC) d += e.efc_D[fr];
+    if (lr >= 0 && e.c.efc_state[lr] == ST_QUADRATIC) d += e.efc_D[lr];
+    e.c.hdiag[i] = d;
   }
   g.sync();
-  KM_FOR(w, D::NV * (D::NV + 1) / 2) {
-    // unrank the lower-triangle index: w = i (i + 1) / 2 + j
-    int i = (int)((Num<float>::sqrt(8.0f * (float)w + 1.0f) - 1.0f) * 0.5f);
-    while (i * (i + 1) / 2 > w) i--;
-    while ((i + 1) * (i + 2) / 2 <= w) i++;
-    const int j = w - i * (i + 1) / 2;
-    T h;
-    if (i < D::NVA) h = e.M[i][j];
-    else h = i == j ? (i - D::NVA < 3 ? m.cube_mass : m.cube_inertia[i - D::NVA - 3]) : T(0);
-    if (i == j)
-      for (int r = 0; r < base; r++)
-        if (efc_id(e.efc_desc[r]) == i && e.efc_state[r] == ST_QUADRATIC) h += e.efc_D[r];
-    for (int c = 0; c < e.ncon; c++) {
-      const unsigned sup = e.con_sup[c];
-      if (((sup >> i) & 1u) && ((sup >> j) & 1u)) {
-        const T ni = e.Jc[c][0][i], nj = e.Jc[c][0][j];
-        T acc = e.cb[c][0] * ni * nj;
-        for (int k = 1; k < 4; k++) {
-          const T ki = e.Jc[c][k][i], kj = e.Jc[c][k][j];
-          acc += e.cb[c][k] * (ni * kj + ki * nj) + e.con_W[c][k - 1] * ki * kj;
-        }
-        h += acc;
-      }
-    }
-    e.H[i][j] = h;
-  }
-  KM_FOR(i, D::NV) e.Mgrad[i] = e.grad[i];
-  g.sync();
-  chol_factor<S, T, G>(&e.H[0][0], e.Hd, D::NV, D::HS, g);
-  chol_solve<S, T, G>(&e.H[0][0], e.Hd, e.Mgrad, D::NV, D::HS, g);
+  assemble_h<S, T, G>(e, m, g, true);
+  if (e.coupled) solve_spd<S, T, G, true>(e, m, g, e.c.grad, e.c.Mgrad);
+  else solve_spd<S, T, G, false>(e, m, g, e.c.grad, e.c.Mgrad);
 }
 
 // derivatives of the 1-D cost along the search direction at step alpha
 KM_TPL KM_FN void ls_eval(KM_ARGS, T qg1, T qg2, T alpha, T* d1, T* d2) {
   T q1 = 0, q2 = 0;
   KM_FOR(r, e.nefc) {
-    const T jv = e.efc_jv[r], jar = e.efc_jar[r], x = jar + alpha * jv, Dr = e.efc_D[r];
-    if (efc_type(e.efc_desc[r]) == EFC_FRICTION) {
-      const T f = e.efc_floss[r], rf = e.efc_R[r] * f;
+    const T jv = e.efc_jv[r], jar = e.c.efc_jar[r], x = jar + alpha * jv, Dr = e.efc_D[r];
+    if (r < Dim<S>::NFRIC) {
+      const T f = m.fr_loss[r], rf = m.fr_Rf[r];
       if (x <= -rf) { q1 += -f * jv; continue; }
       if (x >= rf) { q1 += f * jv; continue; }
     } else if (x >= T(0)) continue;
@@ -618,15 +708,15 @@ KM_TPL KM_FN T sol_linesearch(KM_ARGS, T scale) {
   typedef Dim<S> D;
   typedef Num<T> N;
   T sn = 0;
-  KM_FOR(i, D::NV) sn += e.search[i] * e.search[i];
+  KM_FOR(i, D::NV) sn += e.c.search[i] * e.c.search[i];
   const T snorm = N::sqrt(g.sum(sn));
   if (snorm < N::minval()) return 0;
-  mul_M<S, T, G>(e, m, g, e.search, e.Mv);
-  mul_J<S, T, G>(e, m, g, e.search, e.efc_jv);
+  mul_M<S, T, G>(e, m, g, e.c.search, e.c.Mv);
+  mul_J<S, T, G>(e, m, g, e.c.search, e.efc_jv);
   T a1 = 0, a2 = 0;
   KM_FOR(i, D::NV) {
-    a1 += e.search[i] * (e.Ma[i] - e.qfrc_smooth[i]);
-    a2 += T(0.5) * e.search[i] * e.Mv[i];
+    a1 += e.c.search[i] * (e.c.Ma[i] - e.qfrc_smooth[i]);
+    a2 += T(0.5) * e.c.search[i] * e.c.Mv[i];
   }
   const T qg1 = g.sum(a1), qg2 = g.sum(a2);
   T d1, d2;
@@ -662,9 +752,9 @@ KM_TPL KM_FN void fwd_constraint(KM_ARGS) {
   const T cw = total_cost<S, T, G>(e, m, g, e.warm), cs = total_cost<S, T, G>(e, m, g, e.qacc_smooth);
   KM_FOR(i, D::NV) e.qacc[i] = cw > cs ? e.qacc_smooth[i] : e.warm[i];
   g.sync();
-  mul_M<S, T, G>(e, m, g, e.qacc, e.Ma);
-  mul_J<S, T, G>(e, m, g, e.qacc, e.efc_jar);
-  KM_FOR(r, e.nefc) e.efc_jar[r] -= e.efc_aref[r];
+  mul_M<S, T, G>(e, m, g, e.qacc, e.c.Ma);
+  mul_J<S, T, G>(e, m, g, e.qacc, e.c.efc_jar);
+  KM_FOR(r, e.nefc) e.c.efc_jar[r] -= e.efc_aref[r];
   g.sync();
   const T scale = T(1) / (m.meaninertia * T(D::NV));
   T gauss;
@@ -672,21 +762,22 @@ KM_TPL KM_FN void fwd_constraint(KM_ARGS) {
   int niter = 0;
   while (niter < m.iterations) {
     sol_hessian_dir<S, T, G>(e, m, g);
-    KM_FOR(i, D::NV) e.search[i] = -e.Mgrad[i];
+    KM_FOR(i, D::NV) e.c.search[i] = -e.c.Mgrad[i];
     g.sync();
     const T alpha = sol_linesearch<S, T, G>(e, m, g, scale);
     if (alpha == T(0)) break;
-    KM_FOR(i, D::NV) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
-    KM_FOR(r, e.nefc) e.efc_jar[r] += alpha * e.efc_jv[r];
+    KM_FOR(i, D::NV) { e.qacc[i] += alpha * e.c.search[i]; e.c.Ma[i] += alpha * e.c.Mv[i]; }
+    KM_FOR(r, e.nefc) e.c.efc_jar[r] += alpha * e.efc_jv[r];
     g.sync();
     const T oldcost = cost;
     cost = sol_update<S, T, G>(e, m, g, &gauss);
     T gn = 0;
-    KM_FOR(i, D::NV) gn += e.grad[i] * e.grad[i];
+    KM_FOR(i, D::NV) gn += e.c.grad[i] * e.c.grad[i];
     gn = g.sum(gn);
     niter++;
     if (scale * (oldcost - cost) < m.tol || scale * N::sqrt(gn) < m.tol) break;
   }
+  g.converge();
   KM_FOR(i, D::NV) e.warm[i] = e.qacc[i];
   if (g.lane == 0) e.solver_niter = niter;
   g.sync();
@@ -719,11 +810,11 @@ KM_TPL KM_FN void euler(KM_ARGS) {
   g.sync();
 }
 
-KM_TPL KM_FN void step1(KM_ARGS) {
+KM_TPL KM_HD void step1(KM_ARGS) {
   fwd_position<S, T, G>(e, m, g);
   fwd_velocity<S, T, G>(e, m, g);
 }
-KM_TPL KM_FN void step2(KM_ARGS) {
+KM_TPL KM_HD void step2(KM_ARGS) {
   fwd_actuation_acceleration<S, T, G>(e, m, g);
   fwd_constraint<S, T, G>(e, m, g);
   euler<S, T, G>(e, m, g);
@@ -731,7 +822,7 @@ KM_TPL KM_FN void step2(KM_ARGS) {
 
 // =========================================================================================== task: action decode + IK
 // site pose of arm a from the current link frames
-KM_TPL KM_FN void site_pose(const Env<S, T>& e, const Model<S, T>& m, int a, T* pos, T* mat) {
+KM_TPL KM_HD void site_pose(const Env<S, T>& e, const Model<S, T>& m, int a, T* pos, T* mat) {
   const int l = m.arm_site_link[a];
   T t[3], q[4];
   mulv3(t, e.xmat[l], m.site_pos[a]);
@@ -752,7 +843,7 @@ KM_TPL KM_FN void ik_residual(KM_ARGS, int a, const T* x, T* res) {
     for (int i = 0; i < 3; i++) res[3 + i] = rq[i] * T(0.02);                    // IK_RES_RAD
   }
   KM_FOR(i, n) {
-    res[6 + i] = T(6e-3) * (x[i] - e.ik_qprev[i]);                               // IK_RES_REG_PREV
+    res[6 + i] = T(6e-3) * (x[i] - e.b.ik_qprev[i]);                               // IK_RES_REG_PREV
     res[6 + n + i] = T(2e-6) * (x[i] - m.q_home[m.arm_mask[a][i]]);              // IK_RES_REG_HOME
   }
   g.sync();
@@ -791,7 +882,7 @@ KM_TPL KM_FN void ik_jacobian(KM_ARGS, int a) {
     T jl[3], o3[3];
     mulTv3(jl, R, jr);
     mulv3(o3, Dm, jl);
-    for (int i = 0; i < 3; i++) { e.ik_J[i][c] = jp[i]; e.ik_J[3 + i][c] = -T(0.02) * o3[i]; }   // IK_JAC_RAD
+    for (int i = 0; i < 3; i++) { e.b.ik_J[i][c] = jp[i]; e.b.ik_J[3 + i][c] = -T(0.02) * o3[i]; }   // IK_JAC_RAD
   }
   g.sync();
 }
@@ -803,12 +894,12 @@ KM_TPL KM_FN void ik_jacobian(KM_ARGS, int a) {
 KM_TPL KM_FN void ik_solve(KM_ARGS, int a) {
   typedef Dim<S> D;
   const int n = m.arm_nmask[a], nr = 6 + 2 * n;
-  T* A = &e.H[0][0];
+  T* A = &e.c.H[0][0];
   bool bad = false;
   KM_FOR(i, n) {
     const int j = m.arm_mask[a][i];
     const T x = e.qpos[j];
-    e.ik_x[i] = x; e.ik_qprev[i] = x; e.ik_lo[i] = m.range[j][0]; e.ik_hi[i] = m.range[j][1];
+    e.b.ik_x[i] = x; e.b.ik_qprev[i] = x; e.b.ik_lo[i] = m.range[j][0]; e.b.ik_hi[i] = m.range[j][1];
     bad = bad || x < m.range[j][0] || x > m.range[j][1];
   }
   const bool feasible = !g.any(bad);
@@ -816,49 +907,49 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a) {
   if (feasible) {
     const T lam = T(9e-3 * (6e-3 + 2e-6)), reg = T(9e-3);   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)
     T mu = 0;
-    ik_residual<S, T, G>(e, m, g, a, e.ik_x, e.ik_r);
+    ik_residual<S, T, G>(e, m, g, a, e.b.ik_x, e.b.ik_r);
     ik_jacobian<S, T, G>(e, m, g, a);
     T cs = 0;
-    KM_FOR(k, nr) cs += T(0.5) * e.ik_r[k] * e.ik_r[k];
+    KM_FOR(k, nr) cs += T(0.5) * e.b.ik_r[k] * e.b.ik_r[k];
     T cost = g.sum(cs);
     for (int it = 0; it < m.ik_iters; it++) {
       KM_FOR(i, n) {
         T gi = 0;
-        for (int k = 0; k < 6; k++) gi += e.ik_J[k][i] * e.ik_r[k];
-        gi += reg * e.ik_r[6 + i] + reg * e.ik_r[6 + n + i];
-        e.Mgrad[i] = -gi;
-        e.ik_active[i] = (e.ik_x[i] <= e.ik_lo[i] && gi > T(0)) || (e.ik_x[i] >= e.ik_hi[i] && gi < T(0));
+        for (int k = 0; k < 6; k++) gi += e.b.ik_J[k][i] * e.b.ik_r[k];
+        gi += reg * e.b.ik_r[6 + i] + reg * e.b.ik_r[6 + n + i];
+        e.c.Mgrad[i] = -gi;
+        e.b.ik_active[i] = (e.b.ik_x[i] <= e.b.ik_lo[i] && gi > T(0)) || (e.b.ik_x[i] >= e.b.ik_hi[i] && gi < T(0));
       }
       g.sync();
       KM_FOR(i, n) {
         for (int j = 0; j <= i; j++) {
           T s = 0;
-          if (e.ik_active[i] || e.ik_active[j]) s = i == j ? T(1) : T(0);
+          if (e.b.ik_active[i] || e.b.ik_active[j]) s = i == j ? T(1) : T(0);
           else {
-            for (int k = 0; k < 6; k++) s += e.ik_J[k][i] * e.ik_J[k][j];
+            for (int k = 0; k < 6; k++) s += e.b.ik_J[k][i] * e.b.ik_J[k][j];
             if (i == j) s += lam + mu;
           }
           A[i * D::HS + j] = s;
         }
-        if (e.ik_active[i]) e.Mgrad[i] = 0;
+        if (e.b.ik_active[i]) e.c.Mgrad[i] = 0;
       }
       g.sync();
-      chol_factor<S, T, G>(A, e.Hd, n, D::HS, g);
-      chol_solve<S, T, G>(A, e.Hd, e.Mgrad, n, D::HS, g);
+      chol_factor<S, T, G>(A, e.c.Hd, n, D::HS, g);
+      chol_solve<S, T, G>(A, e.c.Hd, e.c.Mgrad, n, D::HS, g);
       KM_FOR(i, n) {
-        const T xn = tclip(e.ik_x[i] + e.Mgrad[i], e.ik_lo[i], e.ik_hi[i]);
-        e.ik_xn[i] = xn;
+        const T xn = tclip(e.b.ik_x[i] + e.c.Mgrad[i], e.b.ik_lo[i], e.b.ik_hi[i]);
+        e.b.ik_xn[i] = xn;
         e.qpos[m.arm_mask[a][i]] = xn;
       }
       g.sync();
       kinematics<S, T, G>(e, m, g);
-      ik_residual<S, T, G>(e, m, g, a, e.ik_xn, e.ik_rn);
+      ik_residual<S, T, G>(e, m, g, a, e.b.ik_xn, e.b.ik_rn);
       T cn = 0;
-      KM_FOR(k, nr) cn += T(0.5) * e.ik_rn[k] * e.ik_rn[k];
+      KM_FOR(k, nr) cn += T(0.5) * e.b.ik_rn[k] * e.b.ik_rn[k];
       const T costn = g.sum(cn);
       if (costn <= cost) {
-        KM_FOR(i, n) e.ik_x[i] = e.ik_xn[i];
-        KM_FOR(k, nr) e.ik_r[k] = e.ik_rn[k];
+        KM_FOR(i, n) e.b.ik_x[i] = e.b.ik_xn[i];
+        KM_FOR(k, nr) e.b.ik_r[k] = e.b.ik_rn[k];
         g.sync();
         cost = costn;
         ik_jacobian<S, T, G>(e, m, g, a);
@@ -871,10 +962,10 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a) {
   }
   KM_FOR(i, n) {
     const int j = m.arm_mask[a][i];
-    const float q = (float)tclip(e.ik_x[i], e.ik_lo[i], e.ik_hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
+    const float q = (float)tclip(e.b.ik_x[i], e.b.ik_lo[i], e.b.ik_hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
     e.ctrl[j] = (T)q;
-    if (feasible && m.ik_teleport) e.qpos[j] = e.ik_x[i];
-    else e.qpos[j] = e.ik_qprev[i];
+    if (feasible && m.ik_teleport) e.qpos[j] = e.b.ik_x[i];
+    else e.qpos[j] = e.b.ik_qprev[i];
   }
   g.sync();
 }
@@ -1013,7 +1104,7 @@ KM_TPL KM_FN void init_env(KM_ARGS) {
   KM_FOR(w, D::NVA * D::NVA) (&e.M[0][0])[w] = 0;
   KM_FOR(r, D::NFRIC) {
     e.efc_desc[r] = efc_pack(EFC_FRICTION, m.fric_dof[r], 0, 0);
-    e.efc_R[r] = m.fr_R[r]; e.efc_D[r] = m.fr_D[r]; e.efc_B[r] = m.fr_B[r]; e.efc_Kip[r] = 0; e.efc_floss[r] = m.fr_loss[r];
+    e.efc_D[r] = m.fr_D[r];
   }
   if (g.lane == 0) { e.ls_evals = 0; e.solver_niter = 0; e.ncon = 0; e.nlim = 0; e.nefc = D::NFRIC; }
   g.sync();

@@ -81,7 +81,6 @@ template <class S, typename T> struct HostSim : HostSimBase {
     std::string s(name);
     if (s == "xpos") { for (int l = 0; l < D::NVA; l++) for (int i = 0; i < 3; i++) PUT(e.xpos[l][i]); }
     else if (s == "xquat") { for (int l = 0; l < D::NVA; l++) for (int i = 0; i < 4; i++) PUT(e.xquat[l][i]); }
-    else if (s == "xipos") { for (int l = 0; l < D::NVA; l++) for (int i = 0; i < 3; i++) PUT(e.xipos[l][i]); }
     else if (s == "com") { for (int i = 0; i < 3; i++) PUT(e.com[i]); }
     else if (s == "qM") {
       for (int i = 0; i < D::NV; i++) for (int j = 0; j < D::NV; j++) {
@@ -94,12 +93,11 @@ template <class S, typename T> struct HostSim : HostSimBase {
     else if (s == "qfrc_smooth") { for (int i = 0; i < D::NV; i++) PUT(e.qfrc_smooth[i]); }
     else if (s == "qacc_smooth") { for (int i = 0; i < D::NV; i++) PUT(e.qacc_smooth[i]); }
     else if (s == "qacc") { for (int i = 0; i < D::NV; i++) PUT(e.qacc[i]); }
-    else if (s == "qfrc_constraint") { for (int i = 0; i < D::NV; i++) PUT(e.qfc[i]); }
+    else if (s == "qfrc_constraint") { for (int i = 0; i < D::NV; i++) PUT(e.c.qfc[i]); }
     else if (s == "efc_aref") { for (int r = 0; r < e.nefc; r++) PUT(e.efc_aref[r]); }
     else if (s == "efc_D") { for (int r = 0; r < e.nefc; r++) PUT(e.efc_D[r]); }
-    else if (s == "efc_R") { for (int r = 0; r < e.nefc; r++) PUT(e.efc_R[r]); }
-    else if (s == "efc_force") { for (int r = 0; r < e.nefc; r++) PUT(e.efc_force[r]); }
-    else if (s == "efc_state") { for (int r = 0; r < e.nefc; r++) PUT(e.efc_state[r]); }
+    else if (s == "efc_force") { for (int r = 0; r < e.nefc; r++) PUT(e.c.efc_force[r]); }
+    else if (s == "efc_state") { for (int r = 0; r < e.nefc; r++) PUT(e.c.efc_state[r]); }
     else if (s == "efc_J") {
       for (int r = 0; r < e.nefc; r++) {
         T x[D::NV];
@@ -107,7 +105,7 @@ template <class S, typename T> struct HostSim : HostSimBase {
         for (int j = 0; j < D::NV; j++) {
           if (efc_type(d) == EFC_CONTACT) {
             bool on = (e.con_sup[id] >> j) & 1u;
-            T jn = on ? e.Jc[id][0][j] : T(0), jk = on ? e.Jc[id][efc_k(d)][j] : T(0);
+            T jn = on ? jc<S, T>(e, id, 0, j) : T(0), jk = on ? jc<S, T>(e, id, efc_k(d), j) : T(0);
             x[j] = jn + (efc_neg(d) ? -1 : 1) * e.con_mu[id][efc_k(d) - 1] * jk;
           } else x[j] = j == id ? (efc_neg(d) ? T(-1) : T(1)) : T(0);
           PUT(x[j]);

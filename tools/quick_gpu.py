@@ -3,7 +3,7 @@ import os; R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.
 import numpy as np, torch
 from gym_kmanip_b200.batch_sim import BatchSim
 for env, n in (("KManipSoloArmQPos", 4096), ("KManipSoloArm", 8192), ("KManipDualArm", 8192)):
-    for G in (8, 16, 32):
+    for G in (32,):
         sim = BatchSim(env, n, dtype="float32")
         try:
             cfg = sim.configure(G, 0)
