@@ -113,6 +113,22 @@ template <int G> struct Grp {
     return v;
 #endif
   }
+  // CTA-wide phase alignment.  The envs of a CTA are independent, yet marching them through the big phases of a
+  // sub-step together makes the warps of an SM fetch the same instructions at the same time: the hot loop is far
+  // larger than the 32 KB L1.5 instruction cache, and unaligned warps spent over half their stall time waiting for
+  // instruction fetch.  Only called from code every thread of the CTA executes the same number of times.
+  KM_HD void cta_sync() const {
+#if defined(__CUDA_ARCH__)
+    __syncthreads();
+#endif
+  }
+  KM_HD bool cta_any(bool p) const {
+#if defined(__CUDA_ARCH__)
+    return __syncthreads_or(p) != 0;
+#else
+    return p;
+#endif
+  }
   KM_HD void sync() const {
 #if defined(__CUDA_ARCH__)
     __syncwarp(lanes());

@@ -78,21 +78,22 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
     m.jtype[l] = fm->jnt_type[l];
     if (link[p] >= 0) {
       m.parent[l] = link[p];
-      for (int i = 0; i < 3; i++) m.lpos[l][i] = (T)fm->body_pos[3 * b + i];
-      for (int i = 0; i < 4; i++) m.lquat[l][i] = (T)fm->body_quat[4 * b + i];
+      for (int i = 0; i < 3; i++) { m.lpos[l][i] = (T)fm->body_pos[3 * b + i]; m.dk_lpos[l][i] = fm->body_pos[3 * b + i]; }
+      for (int i = 0; i < 4; i++) { m.lquat[l][i] = (T)fm->body_quat[4 * b + i]; m.dk_lquat[l][i] = fm->body_quat[4 * b + i]; }
       depth[l] = depth[link[p]] + 1;
     } else {
       KM_FILL_CHECK(!moving[p], "a link's parent is another link or a static body");
       const Pose w = fill_detail::compose(world[p], fm->body_pos + 3 * b, fm->body_quat + 4 * b);
       m.parent[l] = -1;
-      for (int i = 0; i < 3; i++) m.lpos[l][i] = (T)w.p[i];
-      for (int i = 0; i < 4; i++) m.lquat[l][i] = (T)w.q[i];
+      for (int i = 0; i < 3; i++) { m.lpos[l][i] = (T)w.p[i]; m.dk_lpos[l][i] = w.p[i]; }
+      for (int i = 0; i < 4; i++) { m.lquat[l][i] = (T)w.q[i]; m.dk_lquat[l][i] = w.q[i]; }
     }
     KM_FILL_CHECK(fm->dof_parentid[l] == m.parent[l], "dof tree must mirror the link tree");
     m.mass[l] = (T)fm->body_mass[b];
     total_mass += fm->body_mass[b];
     for (int i = 0; i < 3; i++) { m.ipos[l][i] = (T)fm->body_ipos[3 * b + i]; m.inertia[l][i] = (T)fm->body_inertia[3 * b + i]; }
     m.range[l][0] = (T)fm->jnt_range[2 * l]; m.range[l][1] = (T)fm->jnt_range[2 * l + 1];
+    m.dk_range[l][0] = fm->jnt_range[2 * l]; m.dk_range[l][1] = fm->jnt_range[2 * l + 1];
     m.lim_invw[l] = (T)fm->dof_invweight0[l];
     for (int i = 0; i < 2; i++) m.lim_solref[l][i] = (T)fm->jnt_solref[2 * l + i];
     for (int i = 0; i < 5; i++) m.lim_solimp[l][i] = (T)fm->jnt_solimp[5 * l + i];
@@ -222,12 +223,25 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
       m.arm_mask[a][i] = tk->arm_mask[a][i];
       KM_FILL_CHECK((m.ancmask[link[hb]] >> tk->arm_mask[a][i]) & 1u, "masked joints must lie on the site's chain");
     }
+    // chain from the base to the site link, for the fp64 IK
+    {
+      int chain[D::MAXLEVEL], nc = 0;
+      for (int l = link[hb]; l >= 0; l = m.parent[l]) chain[nc++] = l;
+      m.arm_nchain[a] = nc;
+      for (int k = 0; k < nc; k++) {
+        const int l = chain[nc - 1 - k];
+        m.arm_chain[a][k] = l; m.arm_chain_mask[a][k] = -1;
+        for (int i = 0; i < tk->arm_nmask[a]; i++) if (tk->arm_mask[a][i] == l) { m.arm_chain_mask[a][k] = i; m.arm_mask_chain[a][i] = k; }
+      }
+      for (int i = 0; i < 3; i++) m.dk_site_pos[a][i] = off.p[i];
+      for (int i = 0; i < 4; i++) m.dk_site_quat[a][i] = off.q[i];
+    }
     m.arm_grip[a][0] = tk->arm_grip[a][0]; m.arm_grip[a][1] = tk->arm_grip[a][1];
     m.arm_mocap[a] = tk->arm_mocap[a];
     m.off_pos[a] = tk->off_pos[a]; m.off_orn[a] = tk->off_orn[a]; m.off_grip[a] = tk->off_grip[a]; m.off_q[a] = tk->off_q[a];
   }
   m.ik_iters = tk->ik_iters; m.ik_teleport = tk->ik_teleport; m.max_episode_steps = tk->max_episode_steps;
-  for (int i = 0; i < D::QLEN; i++) m.q_home[i] = (T)tk->q_home[i];
+  for (int i = 0; i < D::QLEN; i++) { m.q_home[i] = (T)tk->q_home[i]; m.dk_qhome[i] = tk->q_home[i]; }
   for (int i = 0; i < 3; i++) {
     m.spawn_lo[i] = (T)tk->cube_spawn_lo[i]; m.spawn_hi[i] = (T)tk->cube_spawn_hi[i];
     m.spawn_lo_d[i] = tk->cube_spawn_lo[i]; m.spawn_hi_d[i] = tk->cube_spawn_hi[i];

@@ -110,13 +110,17 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
       __syncwarp();
       g.wmask = __all_sync(0xffffffffu, valid) ? 0xffffffffu : g.mask;
     }
-    if (!valid) continue;
-    load_state<S, T, G>(e, a, env, g);
-    env_step<S, T, G>(e, m, g, a.act + env * m.act_dim, o, env, a.autoreset, a.seed, a.env0);
-    store_state<S, T, G>(e, a, env, g);
-    if (g.lane == 0) {
-      if (a.niter) a.niter[env] = e.solver_niter;
-      if (a.ls) a.ls[env] = e.ls_evals;
+    // env slots past the end of the batch shadow the tile's first env (the CTA marches in phase) and store nothing
+    const long envc = valid ? env : tile;
+    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON};
+    load_state<S, T, G>(e, a, envc, g);
+    env_step<S, T, G>(e, m, g, a.act + envc * m.act_dim, valid ? o : none, envc, a.autoreset, a.seed, a.env0);
+    if (valid) {
+      store_state<S, T, G>(e, a, env, g);
+      if (g.lane == 0) {
+        if (a.niter) a.niter[env] = e.solver_niter;
+        if (a.ls) a.ls[env] = e.ls_evals;
+      }
     }
     g.sync();
   }

@@ -85,6 +85,9 @@ template <class S, typename T> struct Model {
   int arm_nmask[2], arm_mask[2][D::MAXMASK], arm_grip[2][2], arm_site_link[2], arm_mocap[2];
   int off_pos[2], off_orn[2], off_grip[2], off_q[2];
   T site_pos[2][3], site_quat[2][4];              // end-effector site frame in its link
+  // fp64 copies for the IK (kinematic chain of each arm from its base to the site link)
+  int arm_nchain[2], arm_chain[2][D::MAXLEVEL], arm_chain_mask[2][D::MAXLEVEL], arm_mask_chain[2][D::MAXMASK];
+  double dk_lpos[D::NVA][3], dk_lquat[D::NVA][4], dk_site_pos[2][3], dk_site_quat[2][4], dk_range[D::NVA][2], dk_qhome[D::QLEN];
   int ik_iters, ik_teleport, max_episode_steps;
   T q_home[D::QLEN], spawn_lo[3], spawn_hi[3], cube_quat0[4], mocap0[D::NMOCAP * 7];
   double spawn_lo_d[3], spawn_hi_d[3];
@@ -118,19 +121,18 @@ template <class S, typename T> struct Env {
   T efc_D[D::MAXEFC], efc_aref[D::MAXEFC], efc_jv[D::MAXEFC];
   T lim_B[D::NVA], lim_Kip[D::NVA];
   T bias[D::NV], qfrc_smooth[D::NV], qacc_smooth[D::NV], qacc[D::NV];
-  T ik_goal[2][7];
   T obs[D::OBS];
   int solver_niter, ls_evals;                     // diagnostics of the last sub-step
   // Scratch that is live in disjoint phases shares storage:
-  //   a: position/velocity stage (step1)   b: IK between step1 and step2 (also uses c.H, c.Hd, c.Mgrad)
-  //   c: Newton solver (step2); its first three arrays are at least as large as b, which may only overlay those
+  //   a: position/velocity stage (step1)   b: IK between step1 and step2   c: Newton solver (step2)
   struct StageA {
     T cdof[D::NVA][6], cinert[D::NVA][10], cvel[D::NVA][6], cdof_dot[D::NVA][6], cfrc[D::NVA][6];
   };
-  struct StageB {
-    T ik_J[6][D::MAXMASK], ik_r[D::NRES], ik_rn[D::NRES], ik_x[D::MAXMASK], ik_xn[D::MAXMASK], ik_lo[D::MAXMASK],
-        ik_hi[D::MAXMASK], ik_qprev[D::MAXMASK];
-    int ik_active[D::MAXMASK];
+  struct StageB {   // IK runs in fp64 in both builds (km_sim.cuh)
+    double ax[D::MAXLEVEL][3], an[D::MAXLEVEL][3], spos[3], smat[9], goal[7];
+    double J[6][D::MAXMASK], r[D::NRES], rn[D::NRES], x[D::MAXMASK], xn[D::MAXMASK], lo[D::MAXMASK], hi[D::MAXMASK],
+        qprev[D::MAXMASK], A[D::MAXMASK][D::MAXMASK], gv[D::MAXMASK];
+    int active[D::MAXMASK];
   };
   struct StageC {
     T efc_jar[D::MAXEFC], efc_force[D::MAXEFC];
@@ -143,7 +145,6 @@ template <class S, typename T> struct Env {
     StageB b;
     StageC c;
   };
-  static_assert(sizeof(StageB) <= offsetof(StageC, Ma), "IK scratch may only overlay the solver's row arrays");
 };
 
 // efc row descriptor: type | id << 2 | k << 10 | neg << 12   (id = dof for friction/limit rows, contact for contact rows;

@@ -504,8 +504,11 @@ KM_TPL KM_FN void mul_M(KM_ARGS, const T* x, T* out) {
 
 KM_TPL KM_HD void fwd_position(KM_ARGS) {
   typedef Dim<S> D;
+  g.cta_sync();
   kinematics<S, T, G>(e, m, g);
+  g.cta_sync();
   com_crb<S, T, G>(e, m, g);
+  g.cta_sync();
   collision<S, T, G>(e, m, g);
   make_constraint<S, T, G>(e, m, g);
   KM_FOR(i, D::NU) e.actlen[i] = e.qpos[i];   // mj_transmission: joint transmissions, gear 1
@@ -760,22 +763,29 @@ KM_TPL KM_FN void fwd_constraint(KM_ARGS) {
   T gauss;
   T cost = sol_update<S, T, G>(e, m, g, &gauss);
   int niter = 0;
-  while (niter < m.iterations) {
-    sol_hessian_dir<S, T, G>(e, m, g);
-    KM_FOR(i, D::NV) e.c.search[i] = -e.c.Mgrad[i];
-    g.sync();
-    const T alpha = sol_linesearch<S, T, G>(e, m, g, scale);
-    if (alpha == T(0)) break;
-    KM_FOR(i, D::NV) { e.qacc[i] += alpha * e.c.search[i]; e.c.Ma[i] += alpha * e.c.Mv[i]; }
-    KM_FOR(r, e.nefc) e.c.efc_jar[r] += alpha * e.efc_jv[r];
-    g.sync();
-    const T oldcost = cost;
-    cost = sol_update<S, T, G>(e, m, g, &gauss);
-    T gn = 0;
-    KM_FOR(i, D::NV) gn += e.c.grad[i] * e.c.grad[i];
-    gn = g.sum(gn);
-    niter++;
-    if (scale * (oldcost - cost) < m.tol || scale * N::sqrt(gn) < m.tol) break;
+  bool done = niter >= m.iterations;
+  // Newton iterations, marched CTA-wide: envs that have converged idle at the vote until the slowest is done
+  while (true) {
+    if (!done) {
+      sol_hessian_dir<S, T, G>(e, m, g);
+      KM_FOR(i, D::NV) e.c.search[i] = -e.c.Mgrad[i];
+      g.sync();
+      const T alpha = sol_linesearch<S, T, G>(e, m, g, scale);
+      if (alpha == T(0)) done = true;
+      else {
+        KM_FOR(i, D::NV) { e.qacc[i] += alpha * e.c.search[i]; e.c.Ma[i] += alpha * e.c.Mv[i]; }
+        KM_FOR(r, e.nefc) e.c.efc_jar[r] += alpha * e.efc_jv[r];
+        g.sync();
+        const T oldcost = cost;
+        cost = sol_update<S, T, G>(e, m, g, &gauss);
+        T gn = 0;
+        KM_FOR(i, D::NV) gn += e.c.grad[i] * e.c.grad[i];
+        gn = g.sum(gn);
+        niter++;
+        done = scale * (oldcost - cost) < m.tol || scale * N::sqrt(gn) < m.tol || niter >= m.iterations;
+      }
+    }
+    if (!g.cta_any(!done)) break;
   }
   g.converge();
   KM_FOR(i, D::NV) e.warm[i] = e.qacc[i];
@@ -812,10 +822,13 @@ KM_TPL KM_FN void euler(KM_ARGS) {
 
 KM_TPL KM_HD void step1(KM_ARGS) {
   fwd_position<S, T, G>(e, m, g);
+  g.cta_sync();
   fwd_velocity<S, T, G>(e, m, g);
 }
 KM_TPL KM_HD void step2(KM_ARGS) {
+  g.cta_sync();
   fwd_actuation_acceleration<S, T, G>(e, m, g);
+  g.cta_sync();
   fwd_constraint<S, T, G>(e, m, g);
   euler<S, T, G>(e, m, g);
 }
@@ -829,145 +842,6 @@ KM_TPL KM_HD void site_pose(const Env<S, T>& e, const Model<S, T>& m, int a, T* 
   for (int i = 0; i < 3; i++) pos[i] = e.xpos[l][i] + t[i];
   qmul(q, e.xquat[l], m.site_quat[a]);
   q2mat(mat, q);
-}
-
-// ik_res (reference ik_mujoco.py:20-53) at the joint values currently in qpos (kinematics must be fresh)
-KM_TPL KM_FN void ik_residual(KM_ARGS, int a, const T* x, T* res) {
-  const int n = m.arm_nmask[a];
-  if (g.lane == 0) {
-    T pos[3], mat[9], cur[4], rq[3];
-    site_pose<S, T, G>(e, m, a, pos, mat);
-    for (int i = 0; i < 3; i++) res[i] = pos[i] - e.ik_goal[a][i];
-    mat2quat(cur, mat);
-    subquat(rq, e.ik_goal[a] + 3, cur);
-    for (int i = 0; i < 3; i++) res[3 + i] = rq[i] * T(0.02);                    // IK_RES_RAD
-  }
-  KM_FOR(i, n) {
-    res[6 + i] = T(6e-3) * (x[i] - e.b.ik_qprev[i]);                               // IK_RES_REG_PREV
-    res[6 + n + i] = T(2e-6) * (x[i] - m.q_home[m.arm_mask[a][i]]);              // IK_RES_REG_HOME
-  }
-  g.sync();
-}
-
-// pose rows of ik_jac (reference ik_mujoco.py:56-97): [Jp ; rad * d subQuat(goal, cur) / dq], columns = mask.
-// The orientation block is -rad * Jl^{-1}(phi) R_site^T Jr with phi = subQuat(goal, cur)  (DESIGN.md).
-KM_TPL KM_FN void ik_jacobian(KM_ARGS, int a) {
-  typedef Num<T> N;
-  const int n = m.arm_nmask[a];
-  KM_FOR(c, n) {
-    T pos[3], R[9], cur[4], phi[3];
-    site_pose<S, T, G>(e, m, a, pos, R);
-    mat2quat(cur, R);
-    subquat(phi, e.ik_goal[a] + 3, cur);
-    T u[3] = {phi[0], phi[1], phi[2]};
-    const T half = T(0.5) * normalize3(u);
-    const T coef = T(1) - (half < T(6e-8) ? T(1) : half / N::tan(half));
-    const T K[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
-    T Dm[9];
-    for (int i = 0; i < 3; i++)
-      for (int j = 0; j < 3; j++) {
-        T kk = 0;
-        for (int k = 0; k < 3; k++) kk += K[3 * i + k] * K[3 * k + j];
-        Dm[3 * i + j] = (i == j ? T(1) : T(0)) - half * K[3 * i + j] + coef * kk;
-      }
-    const int j = m.arm_mask[a][c];
-    const T ax[3] = {e.xmat[j][2], e.xmat[j][5], e.xmat[j][8]};
-    T jp[3], jr[3] = {0, 0, 0};
-    if (m.jtype[j] == JT_SLIDE) { jp[0] = ax[0]; jp[1] = ax[1]; jp[2] = ax[2]; }
-    else {
-      const T o[3] = {pos[0] - e.xpos[j][0], pos[1] - e.xpos[j][1], pos[2] - e.xpos[j][2]};
-      cross3(jp, ax, o);
-      jr[0] = ax[0]; jr[1] = ax[1]; jr[2] = ax[2];
-    }
-    T jl[3], o3[3];
-    mulTv3(jl, R, jr);
-    mulv3(o3, Dm, jl);
-    for (int i = 0; i < 3; i++) { e.b.ik_J[i][c] = jp[i]; e.b.ik_J[3 + i][c] = -T(0.02) * o3[i]; }   // IK_JAC_RAD
-  }
-  g.sync();
-}
-
-// Device IK: projected Levenberg-Marquardt on the reference's stationarity condition J^T r = 0 with J, r
-// exactly as ik_jac / ik_res build them (including their mismatched regulariser weights),
-// a fixed iteration count, the bound handling of scipy's TRF at its KKT point, and the reference's side
-// effect of leaving qpos[mask] at the solution (B-1).  Skipped when x0 is out of bounds (B-4).
-KM_TPL KM_FN void ik_solve(KM_ARGS, int a) {
-  typedef Dim<S> D;
-  const int n = m.arm_nmask[a], nr = 6 + 2 * n;
-  T* A = &e.c.H[0][0];
-  bool bad = false;
-  KM_FOR(i, n) {
-    const int j = m.arm_mask[a][i];
-    const T x = e.qpos[j];
-    e.b.ik_x[i] = x; e.b.ik_qprev[i] = x; e.b.ik_lo[i] = m.range[j][0]; e.b.ik_hi[i] = m.range[j][1];
-    bad = bad || x < m.range[j][0] || x > m.range[j][1];
-  }
-  const bool feasible = !g.any(bad);
-  g.sync();
-  if (feasible) {
-    const T lam = T(9e-3 * (6e-3 + 2e-6)), reg = T(9e-3);   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)
-    T mu = 0;
-    ik_residual<S, T, G>(e, m, g, a, e.b.ik_x, e.b.ik_r);
-    ik_jacobian<S, T, G>(e, m, g, a);
-    T cs = 0;
-    KM_FOR(k, nr) cs += T(0.5) * e.b.ik_r[k] * e.b.ik_r[k];
-    T cost = g.sum(cs);
-    for (int it = 0; it < m.ik_iters; it++) {
-      KM_FOR(i, n) {
-        T gi = 0;
-        for (int k = 0; k < 6; k++) gi += e.b.ik_J[k][i] * e.b.ik_r[k];
-        gi += reg * e.b.ik_r[6 + i] + reg * e.b.ik_r[6 + n + i];
-        e.c.Mgrad[i] = -gi;
-        e.b.ik_active[i] = (e.b.ik_x[i] <= e.b.ik_lo[i] && gi > T(0)) || (e.b.ik_x[i] >= e.b.ik_hi[i] && gi < T(0));
-      }
-      g.sync();
-      KM_FOR(i, n) {
-        for (int j = 0; j <= i; j++) {
-          T s = 0;
-          if (e.b.ik_active[i] || e.b.ik_active[j]) s = i == j ? T(1) : T(0);
-          else {
-            for (int k = 0; k < 6; k++) s += e.b.ik_J[k][i] * e.b.ik_J[k][j];
-            if (i == j) s += lam + mu;
-          }
-          A[i * D::HS + j] = s;
-        }
-        if (e.b.ik_active[i]) e.c.Mgrad[i] = 0;
-      }
-      g.sync();
-      chol_factor<S, T, G>(A, e.c.Hd, n, D::HS, g);
-      chol_solve<S, T, G>(A, e.c.Hd, e.c.Mgrad, n, D::HS, g);
-      KM_FOR(i, n) {
-        const T xn = tclip(e.b.ik_x[i] + e.c.Mgrad[i], e.b.ik_lo[i], e.b.ik_hi[i]);
-        e.b.ik_xn[i] = xn;
-        e.qpos[m.arm_mask[a][i]] = xn;
-      }
-      g.sync();
-      kinematics<S, T, G>(e, m, g);
-      ik_residual<S, T, G>(e, m, g, a, e.b.ik_xn, e.b.ik_rn);
-      T cn = 0;
-      KM_FOR(k, nr) cn += T(0.5) * e.b.ik_rn[k] * e.b.ik_rn[k];
-      const T costn = g.sum(cn);
-      if (costn <= cost) {
-        KM_FOR(i, n) e.b.ik_x[i] = e.b.ik_xn[i];
-        KM_FOR(k, nr) e.b.ik_r[k] = e.b.ik_rn[k];
-        g.sync();
-        cost = costn;
-        ik_jacobian<S, T, G>(e, m, g, a);
-        mu = mu * T(0.25);
-        if (mu < T(1e-6)) mu = 0;
-      } else {
-        mu = mu == T(0) ? T(1e-4) : mu * T(4);
-      }
-    }
-  }
-  KM_FOR(i, n) {
-    const int j = m.arm_mask[a][i];
-    const float q = (float)tclip(e.b.ik_x[i], e.b.ik_lo[i], e.b.ik_hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
-    e.ctrl[j] = (T)q;
-    if (feasible && m.ik_teleport) e.qpos[j] = e.b.ik_x[i];
-    else e.qpos[j] = e.b.ik_qprev[i];
-  }
-  g.sync();
 }
 
 // scipy Rotation.from_matrix(R).as_euler("xyz") (extrinsic), then from_euler("xyz", e).as_quat()[[3,0,1,2]]
@@ -989,6 +863,197 @@ template <typename T> KM_HD void euler_xyz_ext_to_quat(T* q, const T* eul) {
   qmul(q, qz, t);
 }
 
+// ---- inverse kinematics.  All IK arithmetic is fp64 in both builds: the problem is regularised only by
+// lam ~ 5e-5 along the arm's null space, so fp32 evaluation noise of the chain kinematics (1e-7 m) would move the
+// solution by ~1e-4 rad, which the kp = 1000 servos then turn into visible velocity differences.  The chain is
+// serial anyway (one lane sweeps it); the per-column work is spread over the lanes.
+
+// forward kinematics of arm a's chain at joint values b.x (masked joints) / qpos (the others): per-link axis and
+// anchor, site pose.  One lane.
+KM_TPL KM_HD void ik_chain_fk(Env<S, T>& e, const Model<S, T>& m, int a, const double* x) {
+  typedef Num<double> N;
+  double q[4] = {1, 0, 0, 0}, pos[3] = {0, 0, 0}, mat[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int k = 0; k < m.arm_nchain[a]; k++) {
+    const int l = m.arm_chain[a][k], mi = m.arm_chain_mask[a][k];
+    double t[3], ql[4];
+    mulv3(t, mat, m.dk_lpos[l]);
+    for (int i = 0; i < 3; i++) pos[i] += t[i];
+    qmul(ql, q, m.dk_lquat[l]);
+    const double th = mi >= 0 ? x[mi] : (double)e.qpos[l];
+    if (m.jtype[l] == JT_HINGE) {
+      double s, c;
+      N::sincos(th * 0.5, &s, &c);
+      q[0] = ql[0] * c - ql[3] * s; q[1] = ql[1] * c + ql[2] * s; q[2] = ql[2] * c - ql[1] * s; q[3] = ql[3] * c + ql[0] * s;
+    } else { q[0] = ql[0]; q[1] = ql[1]; q[2] = ql[2]; q[3] = ql[3]; }
+    qnormalize(q);
+    q2mat(mat, q);
+    for (int i = 0; i < 3; i++) { e.b.an[k][i] = pos[i]; e.b.ax[k][i] = mat[3 * i + 2]; }
+    if (m.jtype[l] == JT_SLIDE) { pos[0] += mat[2] * th; pos[1] += mat[5] * th; pos[2] += mat[8] * th; }
+  }
+  double t[3], sq[4];
+  mulv3(t, mat, m.dk_site_pos[a]);
+  for (int i = 0; i < 3; i++) e.b.spos[i] = pos[i] + t[i];
+  qmul(sq, q, m.dk_site_quat[a]);
+  q2mat(e.b.smat, sq);
+}
+
+// ik_res (reference ik_mujoco.py:20-53) from the chain pose currently in e.b; pose rows by lane 0, regularisers by all
+KM_TPL KM_HD void ik_residual(KM_ARGS, int a, const double* x, double* res) {
+  const int n = m.arm_nmask[a];
+  if (g.lane == 0) {
+    double cur[4], rq[3];
+    for (int i = 0; i < 3; i++) res[i] = e.b.spos[i] - e.b.goal[i];
+    mat2quat(cur, e.b.smat);
+    subquat(rq, e.b.goal + 3, cur);
+    for (int i = 0; i < 3; i++) res[3 + i] = rq[i] * 0.02;                        // IK_RES_RAD
+  }
+  KM_FOR(i, n) {
+    res[6 + i] = 6e-3 * (x[i] - e.b.qprev[i]);                                     // IK_RES_REG_PREV
+    res[6 + n + i] = 2e-6 * (x[i] - m.dk_qhome[m.arm_mask[a][i]]);                 // IK_RES_REG_HOME
+  }
+  g.sync();
+}
+
+// pose rows of ik_jac (reference ik_mujoco.py:56-97): [Jp ; rad * d subQuat(goal, cur) / dq], columns = mask.
+// The orientation block is -rad * Jl^{-1}(phi) R_site^T Jr with phi = subQuat(goal, cur)  (DESIGN.md).
+KM_TPL KM_HD void ik_jacobian(KM_ARGS, int a) {
+  typedef Num<double> N;
+  const int n = m.arm_nmask[a];
+  KM_FOR(c, n) {
+    const double* R = e.b.smat;
+    double cur[4], phi[3];
+    mat2quat(cur, R);
+    subquat(phi, e.b.goal + 3, cur);
+    double u[3] = {phi[0], phi[1], phi[2]};
+    const double half = 0.5 * normalize3(u);
+    const double coef = 1.0 - (half < 6e-8 ? 1.0 : half / N::tan(half));
+    const double K[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
+    double Dm[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double kk = 0;
+        for (int k = 0; k < 3; k++) kk += K[3 * i + k] * K[3 * k + j];
+        Dm[3 * i + j] = (i == j ? 1.0 : 0.0) - half * K[3 * i + j] + coef * kk;
+      }
+    const int k = m.arm_mask_chain[a][c];   // position of masked joint c in the chain
+    const double* ax = e.b.ax[k];
+    double jp[3], jr[3] = {0, 0, 0};
+    if (m.jtype[m.arm_mask[a][c]] == JT_SLIDE) { jp[0] = ax[0]; jp[1] = ax[1]; jp[2] = ax[2]; }
+    else {
+      const double o[3] = {e.b.spos[0] - e.b.an[k][0], e.b.spos[1] - e.b.an[k][1], e.b.spos[2] - e.b.an[k][2]};
+      cross3(jp, ax, o);
+      jr[0] = ax[0]; jr[1] = ax[1]; jr[2] = ax[2];
+    }
+    double jl[3], o3[3];
+    mulTv3(jl, R, jr);
+    mulv3(o3, Dm, jl);
+    for (int i = 0; i < 3; i++) { e.b.J[i][c] = jp[i]; e.b.J[3 + i][c] = -0.02 * o3[i]; }   // IK_JAC_RAD
+  }
+  g.sync();
+}
+
+// Device IK of one arm, fused in front of the sub-steps: end-effector target from the action (reference
+// env_sim.py:60-70, 80-90), then projected Levenberg-Marquardt on the reference's stationarity condition J^T r = 0
+// with J, r exactly as ik_jac / ik_res build them (including their mismatched regulariser weights),
+// a fixed iteration count, the bound handling of scipy's TRF at its KKT point, and the reference's side effect of
+// leaving qpos[mask] at the solution (B-1).  Skipped when x0 is out of bounds (B-4).
+KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
+  typedef Dim<S> D;
+  const int n = m.arm_nmask[a], nr = 6 + 2 * n;
+  bool bad = false;
+  KM_FOR(i, n) {
+    const int j = m.arm_mask[a][i];
+    const double x = (double)e.qpos[j];
+    e.b.x[i] = x; e.b.qprev[i] = x; e.b.lo[i] = m.dk_range[j][0]; e.b.hi[i] = m.dk_range[j][1];
+    bad = bad || x < m.dk_range[j][0] || x > m.dk_range[j][1];
+  }
+  const bool feasible = !g.any(bad);
+  g.sync();
+  if (g.lane == 0) {
+    // goal = current site pose displaced by the action (EE_POS_DELTA 0.01, EE_ORN_DELTA 0.1, extrinsic xyz Euler)
+    double eul[3];
+    ik_chain_fk<S, T, G>(e, m, a, e.b.x);
+    for (int i = 0; i < 3; i++) e.b.goal[i] = (double)act[m.off_pos[a] + i] * 0.01 + e.b.spos[i];
+    mat_to_euler_xyz_ext(eul, e.b.smat);
+    for (int i = 0; i < 3; i++) eul[i] = (double)act[m.off_orn[a] + i] * 0.1 + eul[i];
+    euler_xyz_ext_to_quat(e.b.goal + 3, eul);
+    for (int i = 0; i < 7; i++) e.mocap[7 * m.arm_mocap[a] + i] = (T)e.b.goal[i];
+  }
+  g.sync();
+  if (feasible) {
+    const double lam = 9e-3 * (6e-3 + 2e-6), reg = 9e-3;   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)
+    double mu = 0;
+    ik_residual<S, T, G>(e, m, g, a, e.b.x, e.b.r);
+    ik_jacobian<S, T, G>(e, m, g, a);
+    double cs = 0;
+    KM_FOR(k, nr) cs += 0.5 * e.b.r[k] * e.b.r[k];
+    double cost = g.sum(cs);
+    for (int it = 0; it < m.ik_iters; it++) {
+      KM_FOR(i, n) {
+        double gi = 0;
+        for (int k = 0; k < 6; k++) gi += e.b.J[k][i] * e.b.r[k];
+        gi += reg * e.b.r[6 + i] + reg * e.b.r[6 + n + i];
+        e.b.gv[i] = -gi;
+        e.b.active[i] = (e.b.x[i] <= e.b.lo[i] && gi > 0.0) || (e.b.x[i] >= e.b.hi[i] && gi < 0.0);
+      }
+      g.sync();
+      KM_FOR(w, n * n) {
+        const int i = w / n, j = w - i * n;
+        if (j > i) continue;
+        double sacc = 0;
+        if (e.b.active[i] || e.b.active[j]) sacc = i == j ? 1.0 : 0.0;
+        else {
+          for (int k = 0; k < 6; k++) sacc += e.b.J[k][i] * e.b.J[k][j];
+          if (i == j) sacc += lam + mu;
+        }
+        e.b.A[i][j] = sacc;
+      }
+      g.sync();
+      if (g.lane == 0) {   // 7 x 7 Cholesky and the two triangular solves
+        for (int i = 0; i < n; i++) if (e.b.active[i]) e.b.gv[i] = 0;
+        for (int j = 0; j < n; j++) {
+          double d = e.b.A[j][j];
+          for (int k = 0; k < j; k++) d -= e.b.A[j][k] * e.b.A[j][k];
+          d = Num<double>::sqrt(d);
+          e.b.A[j][j] = d;
+          for (int i = j + 1; i < n; i++) {
+            double u = e.b.A[i][j];
+            for (int k = 0; k < j; k++) u -= e.b.A[i][k] * e.b.A[j][k];
+            e.b.A[i][j] = u / d;
+          }
+        }
+        for (int i = 0; i < n; i++) { double t = e.b.gv[i]; for (int k = 0; k < i; k++) t -= e.b.A[i][k] * e.b.gv[k]; e.b.gv[i] = t / e.b.A[i][i]; }
+        for (int i = n - 1; i >= 0; i--) { double t = e.b.gv[i]; for (int k = i + 1; k < n; k++) t -= e.b.A[k][i] * e.b.gv[k]; e.b.gv[i] = t / e.b.A[i][i]; }
+        for (int i = 0; i < n; i++) e.b.xn[i] = tclip(e.b.x[i] + e.b.gv[i], e.b.lo[i], e.b.hi[i]);
+        ik_chain_fk<S, T, G>(e, m, a, e.b.xn);
+      }
+      g.sync();
+      ik_residual<S, T, G>(e, m, g, a, e.b.xn, e.b.rn);
+      double cn = 0;
+      KM_FOR(k, nr) cn += 0.5 * e.b.rn[k] * e.b.rn[k];
+      const double costn = g.sum(cn);
+      if (costn <= cost) {
+        KM_FOR(i, n) e.b.x[i] = e.b.xn[i];
+        KM_FOR(k, nr) e.b.r[k] = e.b.rn[k];
+        g.sync();
+        cost = costn;
+        ik_jacobian<S, T, G>(e, m, g, a);
+        mu = mu * 0.25;
+        if (mu < 1e-6) mu = 0;
+      } else {
+        mu = mu == 0.0 ? 1e-4 : mu * 4.0;
+      }
+    }
+  }
+  KM_FOR(i, n) {
+    const int j = m.arm_mask[a][i];
+    const float q = (float)tclip(e.b.x[i], e.b.lo[i], e.b.hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
+    e.ctrl[j] = (T)q;
+    if (feasible && m.ik_teleport) e.qpos[j] = (T)e.b.x[i];
+  }
+  g.sync();
+}
+
 // KManipTask.before_step (reference env_sim.py:38-108); `act` points at this env's float32 action record
 KM_TPL KM_FN void before_step(KM_ARGS, const float* act) {
   typedef Dim<S> D;
@@ -1007,20 +1072,9 @@ KM_TPL KM_FN void before_step(KM_ARGS, const float* act) {
       }
   }
   if (m.act_mode == 0) {
-    // end-effector targets (env_sim.py:60-70, 80-90) from the site poses of the last position stage
-    KM_FOR(a, m.n_arm) {
-      if (m.off_pos[a] < 0) continue;
-      T pos[3], mat[9], eul[3];
-      site_pose<S, T, G>(e, m, a, pos, mat);
-      for (int i = 0; i < 3; i++) e.ik_goal[a][i] = (T)((double)act[m.off_pos[a] + i] * 0.01) + pos[i];
-      mat_to_euler_xyz_ext(eul, mat);
-      for (int i = 0; i < 3; i++) eul[i] = (T)((double)act[m.off_orn[a] + i] * 0.1) + eul[i];
-      euler_xyz_ext_to_quat(e.ik_goal[a] + 3, eul);
-      for (int i = 0; i < 7; i++) e.mocap[7 * m.arm_mocap[a] + i] = e.ik_goal[a][i];
-    }
-    g.sync();
+    // end-effector targets + IK, right arm then left (env_sim.py:60-99); the arms' chains are independent
     for (int a = 0; a < m.n_arm; a++)
-      if (m.off_pos[a] >= 0) ik_solve<S, T, G>(e, m, g, a);
+      if (m.off_pos[a] >= 0) ik_solve<S, T, G>(e, m, g, a, act);
   } else {
     // joint-position deltas (env_sim.py:100-103)
     for (int a = 0; a < m.n_arm; a++) {
@@ -1121,6 +1175,7 @@ KM_TPL KM_FN void env_step(KM_ARGS, const float* act, const StepOut<T>& o, long 
                            uint64_t env0) {
   typedef Dim<S> D;
   step1<S, T, G>(e, m, g);
+  g.cta_sync();
   before_step<S, T, G>(e, m, g, act);
   step2<S, T, G>(e, m, g);
   for (int s = 1; s < m.nsub; s++) { step1<S, T, G>(e, m, g); step2<S, T, G>(e, m, g); }
