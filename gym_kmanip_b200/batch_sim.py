@@ -119,6 +119,12 @@ class BatchSim:
         _lib.check(self.L.km_step_host(self.h, ptr(action_host), ptr(obs_host), ptr(reward_host), ptr(truncated_host),
                                        int(autoreset)))
 
+    def reset_host(self, mask_host=None, cube_xyz_host=None, obs_host=None):
+        """km_reset_host: reset with HOST buffers (numpy or pinned torch tensors; any may be None)."""
+        def ptr(x):
+            return None if x is None else (x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr())
+        _lib.check(self.L.km_reset_host(self.h, ptr(mask_host), ptr(cube_xyz_host), ptr(obs_host)))
+
     # ------------------------------------------------------------------ state access (teacher forcing, physics shim)
     def get_state(self):
         t = self.torch
@@ -147,7 +153,7 @@ class BatchSim:
     def state_slices(self) -> Dict[str, slice]:
         o, out = 0, {}
         for k, n in (("qpos", self.nq), ("qvel", self.nv), ("ctrl", self.nu), ("warm", self.nv), ("mocap", 7 * self.nmocap),
-                     ("time", 1)):
+                     ("time", 1), ("cube_lo", 3)):
             out[k] = slice(o, o + n)
             o += n
         return out
@@ -155,6 +161,15 @@ class BatchSim:
     def contacts(self):
         _lib.check(self.L.km_contacts(self.h, self.ncon.data_ptr(), self.con_geoms.data_ptr(), self._stream()))
         return self.ncon, self.con_geoms
+
+    def site_poses(self):
+        """End-effector site positions [n, n_arm, 3] and rotation matrices [n, n_arm, 3, 3] of the stored state."""
+        t = self.torch
+        na = int(self.L.km_n_arm(self.h))
+        pos = t.empty(self.n, na, 3, dtype=self.tdtype, device=self.device)
+        mat = t.empty(self.n, na, 3, 3, dtype=self.tdtype, device=self.device)
+        _lib.check(self.L.km_site_poses(self.h, pos.data_ptr(), mat.data_ptr(), self._stream()))
+        return pos, mat
 
     def solver_stats(self):
         t = self.torch

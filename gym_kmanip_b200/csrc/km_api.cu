@@ -22,7 +22,7 @@ static thread_local std::string g_err;
 
 struct km_sim {
   KmVtable vt;
-  int scene, dtype, n, device, act_dim;
+  int scene, dtype, n, device, act_dim, n_arm;
   unsigned long long seed, env0;
   int G, epb, grid, ctas_per_sm, num_sms;
   void* d_model;
@@ -117,7 +117,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
     case 5: h->vt = km::vtable_torso_f64(); break;
     default: delete h; return fail(KM_ERR_ARG, "km_create: unknown scene");
   }
-  h->scene = scene; h->dtype = dtype; h->n = n_envs; h->device = device; h->seed = seed; h->env0 = env0; h->act_dim = task->act_dim;
+  h->scene = scene; h->dtype = dtype; h->n = n_envs; h->device = device; h->seed = seed; h->env0 = env0; h->act_dim = task->act_dim; h->n_arm = task->n_arm;
   std::vector<unsigned char> host_model(h->vt.model_bytes);
   std::string err;
   if (h->vt.fill(model, task, host_model.data(), err) != 0) { delete h; return fail(KM_ERR_MODEL, err); }
@@ -249,6 +249,18 @@ int km_contacts(km_handle h, int* ncon_dev, int* con_geoms_dev, void* stream) {
   h->launches++;
   return KM_OK;
 }
+
+int km_site_poses(km_handle h, void* xpos_dev, void* xmat_dev, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  KmArgs a = base_args(h, stream);
+  a.site_pos = xpos_dev; a.site_mat = xmat_dev;
+  KM_CUDA(h->vt.contacts(a));
+  h->launches++;
+  return KM_OK;
+}
+
+int km_n_arm(km_handle h) { return h->n_arm; }
 
 int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream) {
   if (!h) return fail(KM_ERR_ARG, "null handle");

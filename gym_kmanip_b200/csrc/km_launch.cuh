@@ -30,6 +30,8 @@ struct KmArgs {
   int* ls;
   const unsigned char* mask;
   const void* cube_xyz;
+  void* site_pos;
+  void* site_mat;
   int n, autoreset;
   unsigned long long seed, env0;
   int G, epb, grid;
@@ -75,11 +77,11 @@ template <class S, typename T> __device__ __forceinline__ const Model<S, T>& sta
   return *(const Model<S, T>*)smem;
 }
 
-// state record <-> the leading members of Env (qpos, qvel, ctrl, warm, mocap, time are laid out contiguously)
+// state record <-> the leading members of Env (qpos, qvel, ctrl, warm, mocap, time, cube_lo are laid out contiguously)
 template <class S, typename T, int G> __device__ __forceinline__ void load_state(Env<S, T>& e, const KmArgs& a, long env, const Grp<G>& g) {
-  constexpr int SD = Dim<S>::NQ + 2 * Dim<S>::NV + Dim<S>::NU + 7 * Dim<S>::NMOCAP + 1;
+  constexpr int SD = Dim<S>::STATE;
   typedef Env<S, T> E_;
-  static_assert(offsetof(E_, time) == (SD - 1) * sizeof(T), "state members of Env must be contiguous");
+  static_assert(offsetof(E_, time) == (SD - 4) * sizeof(T) && offsetof(E_, cube_lo) == (SD - 3) * sizeof(T), "state members of Env must be contiguous");
   const T* src = (const T*)a.state + env * SD;
   T* dst = (T*)&e;
   KM_FOR(i, SD) dst[i] = src[i];
@@ -87,7 +89,7 @@ template <class S, typename T, int G> __device__ __forceinline__ void load_state
   g.sync();
 }
 template <class S, typename T, int G> __device__ __forceinline__ void store_state(const Env<S, T>& e, const KmArgs& a, long env, const Grp<G>& g) {
-  constexpr int SD = Dim<S>::NQ + 2 * Dim<S>::NV + Dim<S>::NU + 7 * Dim<S>::NMOCAP + 1;
+  constexpr int SD = Dim<S>::STATE;
   T* dst = (T*)a.state + env * SD;
   const T* src = (const T*)&e;
   KM_FOR(i, SD) dst[i] = src[i];
@@ -164,6 +166,14 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
           a.con_geoms[env * 2 * MC + 2 * c] = g1;
           a.con_geoms[env * 2 * MC + 2 * c + 1] = g2;
         }
+      // end-effector site frames (callers read physics.data.site("eer_site_pos").xpos, reference examples/2_synthetic_data.py:34)
+      if (a.site_pos || a.site_mat)
+        for (int arm = 0; arm < m.n_arm; arm++) {
+          T pos[3], mat[9];
+          site_pose<S, T, G>(e, m, arm, pos, mat);
+          if (a.site_pos) for (int i = 0; i < 3; i++) ((T*)a.site_pos)[(env * m.n_arm + arm) * 3 + i] = pos[i];
+          if (a.site_mat) for (int i = 0; i < 9; i++) ((T*)a.site_mat)[(env * m.n_arm + arm) * 9 + i] = mat[i];
+        }
     }
     g.sync();
   }
@@ -207,7 +217,7 @@ template <class S, typename T> struct Launch {
     KmVtable v;
     v.model_bytes = sizeof(Model<S, T>); v.env_bytes = env_smem<S, T>(); v.scalar_bytes = sizeof(T);
     v.nq = D::NQ; v.nv = D::NV; v.nu = D::NU; v.nmocap = D::NMOCAP; v.obs_dim = D::OBS;
-    v.state_dim = D::NQ + 2 * D::NV + D::NU + 7 * D::NMOCAP + 1; v.maxcon = D::MAXCON; v.nlanes_min = D::NV <= 16 ? 16 : 32; v.max_threads = max_threads<S, T>();
+    v.state_dim = D::STATE; v.maxcon = D::MAXCON; v.nlanes_min = D::NV <= 16 ? 16 : 32; v.max_threads = max_threads<S, T>();
     v.fill = &fill; v.step = &step; v.reset = &reset; v.contacts = &contacts; v.prepare = &prepare;
     return v;
   }

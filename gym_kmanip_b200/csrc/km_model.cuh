@@ -36,6 +36,7 @@ template <class S> struct Dim {
   static constexpr int OBS = 2 * S::Q_LEN + 7;
   static constexpr int MAXMASK = 8;
   static constexpr int NRES = 6 + 2 * MAXMASK;
+  static constexpr int STATE = NQ + 2 * NV + NU + 7 * NMOCAP + 1 + 3;   // scalars per state record
   static_assert(NU == NVA, "one position actuator per articulated joint");
   static_assert(NV <= 32, "dof support masks are 32-bit");
 };
@@ -98,6 +99,10 @@ template <class S, typename T> struct Env {
   typedef Dim<S> D;
   // persistent state (what km_get_state / km_set_state expose)
   T qpos[D::NQ], qvel[D::NV], ctrl[D::NU], warm[D::NV], mocap[D::NMOCAP * 7], time;
+  // low-order part of the cube's position: qpos[NVA..NVA+2] + cube_lo is the position.  The cube rests ~1e-7 m deep in
+  // the table (solimp 0.9999), two float32 ulps of its height, so the fp32 build integrates the cube's translation in
+  // float-float arithmetic; always zero in the fp64 build.
+  T cube_lo[3];
   int step, episode;
   // position stage: link frames, cube rotation, mass matrix (articulated block; the cube block is a constant diagonal)
   T xpos[D::NVA][3], xquat[D::NVA][4], xmat[D::NVA][9];

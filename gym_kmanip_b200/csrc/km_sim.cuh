@@ -256,7 +256,7 @@ KM_TPL KM_FN void collision(KM_ARGS) {
       const int l = m.pad_link[s];
       T c1[3], tmp[3], center[3], cl[3], n[3], pb[3];
       mulv3(c1, e.xmat[l], m.pad_pos[s]);
-      for (int i = 0; i < 3; i++) tmp[i] = c1[i] + e.xpos[l][i] - cpos[i];
+      for (int i = 0; i < 3; i++) tmp[i] = (c1[i] + e.xpos[l][i] - cpos[i]) - e.cube_lo[i];
       mulTv3(center, e.cmat, tmp);
       for (int i = 0; i < 3; i++) { cl[i] = tclip(center[i], -m.cube_size[i], m.cube_size[i]); n[i] = cl[i] - center[i]; }
       const T d = N::sqrt(dot3(n, n)), radius = m.pad_rad[s];
@@ -285,7 +285,7 @@ KM_TPL KM_FN void collision(KM_ARGS) {
       }
     } else {             // mjc_PlaneBox: corner i of the cube against z = tab_z, normal (0,0,1)
       const int i = s - D::NPAD;
-      const T pd = cpos[2] - m.tab_z;
+      const T pd = (cpos[2] - m.tab_z) + e.cube_lo[2];   // the difference of the high parts is exact
       T vec[3] = {(i & 1 ? T(1) : T(-1)) * m.cube_size[0], (i & 2 ? T(1) : T(-1)) * m.cube_size[1],
                   (i & 4 ? T(1) : T(-1)) * m.cube_size[2]}, corner[3];
       mulv3(corner, e.cmat, vec);
@@ -799,7 +799,14 @@ KM_TPL KM_FN void euler(KM_ARGS) {
   KM_FOR(i, D::NV) {
     const T v = e.qvel[i] + m.h * e.qacc[i];
     e.qvel[i] = v;
-    if (i < D::NVA + 3) e.qpos[i] += m.h * v;
+    if (sizeof(T) == 4 && i >= D::NVA && i < D::NVA + 3) {
+      // cube translation, float-float: (hi, lo) += h v by an error-free two-sum, then renormalise
+      const T hi = e.qpos[i], p = m.h * v, s = hi + p, bb = s - hi;
+      const T lo = e.cube_lo[i - D::NVA] + ((hi - (s - bb)) + (p - bb));
+      const T hi2 = s + lo;
+      e.qpos[i] = hi2;
+      e.cube_lo[i - D::NVA] = lo - (hi2 - s);
+    } else if (i < D::NVA + 3) e.qpos[i] += m.h * v;
   }
   g.sync();
   if (g.lane == 0) {
@@ -1099,7 +1106,7 @@ KM_TPL KM_FN void observation(KM_ARGS) {
     else if (i < 2 * D::QLEN) v = tclip(e.qvel[i - D::QLEN] / pi, T(-1), T(1));
     else if (i < 2 * D::QLEN + 3) {
       const int k = i - 2 * D::QLEN;
-      v = tclip((e.qpos[D::NVA + k] - m.spawn_lo[k]) / (m.spawn_hi[k] - m.spawn_lo[k]), T(-1), T(1));
+      v = tclip(((e.qpos[D::NVA + k] - m.spawn_lo[k]) + e.cube_lo[k]) / (m.spawn_hi[k] - m.spawn_lo[k]), T(-1), T(1));
     } else v = e.qpos[D::NVA + 3 + (i - 2 * D::QLEN - 3)];
     e.obs[i] = v;
   }
@@ -1140,11 +1147,16 @@ KM_TPL KM_FN void reset_state(KM_ARGS, uint64_t seed, uint64_t env_id, const T* 
   }
   KM_FOR(i, D::NMOCAP * 7) e.mocap[i] = m.mocap0[i];
   if (g.lane == 0) {
-    if (cube_xyz) { for (int i = 0; i < 3; i++) e.qpos[D::NVA + i] = cube_xyz[i]; }
+    if (cube_xyz) { for (int i = 0; i < 3; i++) { e.qpos[D::NVA + i] = cube_xyz[i]; e.cube_lo[i] = 0; } }
     else {
       double u[3];
       spawn_uniforms(seed, env_id, (uint32_t)e.episode, u);
-      for (int i = 0; i < 3; i++) e.qpos[D::NVA + i] = (T)(m.spawn_lo_d[i] + u[i] * (m.spawn_hi_d[i] - m.spawn_lo_d[i]));
+      for (int i = 0; i < 3; i++) {
+        const double x = m.spawn_lo_d[i] + u[i] * (m.spawn_hi_d[i] - m.spawn_lo_d[i]);
+        const T hi = (T)x;
+        e.qpos[D::NVA + i] = hi;
+        e.cube_lo[i] = sizeof(T) == 4 ? (T)(x - (double)hi) : T(0);
+      }
     }
     for (int i = 0; i < 4; i++) e.qpos[D::NVA + 3 + i] = m.cube_quat0[i];
     e.time = 0; e.step = 0;

@@ -143,7 +143,8 @@ def _arr(name: str, vals: List[int], ctype: str = "int") -> str:
     return f"  static constexpr {ctype} {name}[{max(len(vals), 1)}] = {{{', '.join(str(v) for v in (vals or [0]))}}};"
 
 
-def write_scene_header(scene: str, flat: Dict) -> str:
+def render_scene_header(scene: str, flat: Dict) -> str:
+    """Text of csrc/scenes/scene_<scene>.h for a flat model."""
     t = topology(scene, flat)
     S = SCENE_STRUCT[scene]
     lines = [
@@ -165,8 +166,12 @@ def write_scene_header(scene: str, flat: Dict) -> str:
     lines.append("  static constexpr int arm_grip[%d][2] = {%s};" % (
         t["NARM"], ", ".join("{" + ", ".join(map(str, m)) + "}" for m in t["arm_grip"])))
     lines.append("};")
+    return "\n".join(lines) + "\n"
+
+
+def write_scene_header(scene: str, flat: Dict) -> str:
     os.makedirs(SCENE_DIR, exist_ok=True)
     path = os.path.join(SCENE_DIR, f"scene_{scene}.h")
     with open(path, "w") as f:
-        f.write("\n".join(lines) + "\n")
+        f.write(render_scene_header(scene, flat))
     return path

@@ -1,0 +1,100 @@
+"""KManipVectorEnv: the batched env -- N independent envs advanced by one fused CUDA launch per step.
+
+The single-env semantics are those of KManipEnv (reference env_base.py:219-259) under the 64-step TimeLimit of
+``gym.make`` (reference __init__.py:28,247), applied per env with same-step autoreset: on the step an env reaches
+``max_episode_steps`` its ``truncated`` flag is 1, ``info["final_obs"]`` keeps the last observation of the
+finished episode and ``obs`` already holds the first observation of the next one (cube re-spawned from the
+counter-based generator keyed by (seed, global env id, episode)).  All arrays are torch CUDA tensors; observation
+and action dicts use the reference's keys.  Envs shard across GPUs / ranks by contiguous global-id ranges with no
+per-step communication (sharding.py).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Optional
+
+from . import constants as K
+from .batch_sim import BatchSim
+from .flatmodel import action_layout, obs_layout
+from .spaces import Box, Dict as DictSpace
+
+
+class KManipVectorEnv:
+    def __init__(self, env_id: str, num_envs: int, device: int = 0, dtype: str = "float32", seed: int = 0, env0: int = 0,
+                 max_episode_steps: int = K.MAX_EPISODE_STEPS, **sim_kwargs):
+        kw = K.ENV_REGISTRY[env_id]
+        if any("camera" in o for o in kw["obs_list"]):
+            raise NotImplementedError("camera observations are outside the accelerated hot path (SURVEY.md 8f rank 4)")
+        self.env_id, self.num_envs = env_id, int(num_envs)
+        self.sim = BatchSim(env_id, num_envs, device=device, dtype=dtype, seed=seed, env0=env0,
+                            max_episode_steps=max_episode_steps, **sim_kwargs)
+        self.device = self.sim.device
+        self.obs_list, self.act_list = list(kw["obs_list"]), list(kw["act_list"])
+        n_r = len(kw["q_id_r_mask"]) if kw.get("q_id_r_mask") is not None else 0
+        n_l = len(kw["q_id_l_mask"]) if kw.get("q_id_l_mask") is not None else 0
+        self.action_layout = action_layout(self.act_list, n_r, n_l)
+        self.obs_layout = {k: v for k, v in obs_layout(self.sim.q_len).items() if k in self.obs_list}
+        self.single_observation_space = DictSpace(OrderedDict(
+            (k, Box(-1, 1, (sl.stop - sl.start,), K.OBS_DTYPE)) for k, sl in self.obs_layout.items()))
+        self.single_action_space = DictSpace(OrderedDict(
+            (k, Box(-1, 1, (sl.stop - sl.start,), K.ACT_DTYPE)) for k, sl in self.action_layout.items()))
+        t = self.sim.torch
+        self._act = t.zeros(self.num_envs, self.sim.act_dim, dtype=t.float32, device=self.device)
+        self.episode_return = t.zeros(self.num_envs, dtype=t.float64, device=self.device)
+        # running totals of the rollout: sum of rewards, env steps, finished episodes, success steps
+        self.totals = t.zeros(4, dtype=t.float64, device=self.device)
+
+    # -------------------------------------------------------------------------------- helpers
+    def _obs_dict(self, flat) -> "OrderedDict[str, object]":
+        return OrderedDict((k, flat[:, sl]) for k, sl in self.obs_layout.items())
+
+    def flatten_action(self, action):
+        """Dict of [n, k] tensors (reference keys) -> the flat [n, act_dim] float32 record; flat tensors pass through."""
+        t = self.sim.torch
+        if isinstance(action, dict):
+            for k, sl in self.action_layout.items():
+                self._act[:, sl] = t.as_tensor(action[k], device=self.device).to(t.float32).view(self.num_envs, -1)
+            return self._act
+        return action
+
+    def sample_actions(self, generator=None):
+        t = self.sim.torch
+        return t.rand(self.num_envs, self.sim.act_dim, device=self.device, generator=generator) * 2 - 1
+
+    # -------------------------------------------------------------------------------- episode API
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        mask = cube = None
+        if options:
+            mask, cube = options.get("reset_mask"), options.get("cube_xyz")
+        flat = self.sim.reset(mask=mask, cube_xyz=cube)
+        if mask is None:
+            self.episode_return.zero_()
+        else:
+            self.episode_return.masked_fill_(mask.to(self.device).bool(), 0.0)
+        return self._obs_dict(flat), {}
+
+    def step(self, action):
+        t = self.sim.torch
+        flat, rew, term, trunc = self.sim.step(self.flatten_action(action), autoreset=True)
+        success = rew > K.REWARD_SUCCESS_THRESHOLD                   # env_base.py:249
+        done = trunc.bool()
+        self.episode_return += rew.double()
+        info: Dict[str, object] = {
+            "is_success": success, "final_obs": self._obs_dict(self.sim.final_obs),
+            "final_return": t.where(done, self.episode_return, t.zeros_like(self.episode_return)),
+            "con_flags": self.sim.con_flags, "ncon": self.sim.ncon,
+        }
+        self.totals[0] += rew.sum(dtype=t.float64)
+        self.totals[1] += self.num_envs
+        self.totals[2] += done.sum(dtype=t.float64)
+        self.totals[3] += success.sum(dtype=t.float64)
+        self.episode_return.masked_fill_(done, 0.0)
+        return self._obs_dict(flat), rew, term.bool(), done, info
+
+    @property
+    def sim_step_counts(self):
+        _, step, _ = self.sim.get_state()
+        return step
+
+    def close(self):
+        self.sim.close()

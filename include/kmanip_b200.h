@@ -26,7 +26,9 @@
  * serialised by the caller; handles on different devices are independent (env sharding needs no collective).
  *
  * Record layouts (env-major, one contiguous record per env -- the coalesced layout for lane-group-per-env kernels):
- *   state    qpos[nq] qvel[nv] ctrl[nu] qacc_warmstart[nv] mocap[7*nmocap] time   (dtype of the handle: f32 or f64)
+ *   state    qpos[nq] qvel[nv] ctrl[nu] qacc_warmstart[nv] mocap[7*nmocap] time cube_lo[3]   (dtype of the handle)
+ *            cube_lo: low-order part of the cube's position in the f32 build (position = qpos[nq-7..nq-5] + cube_lo;
+ *            the cube rests ~1e-7 m deep in the table, two float32 ulps of its height); always 0 in the f64 build
  *   action   float32[act_dim], keys concatenated in the order of env_base.py:149-190
  *   obs      [q_pos(q_len) q_vel(q_len) cube_pos(3) cube_orn(4)]                    (dtype of the handle)
  */
@@ -136,6 +138,12 @@ void* km_state_ptr(km_handle h);
 
 /* Contacts of the most recent step: runs the position stage on the stored state. */
 int km_contacts(km_handle h, int* ncon_dev, int* con_geoms_dev, void* stream);
+
+/* End-effector site frames of the stored state (position stage only): xpos_dev [n][n_arm][3], xmat_dev [n][n_arm][9]
+   row-major, dtype of the handle; either may be NULL.  Arms in task order (right, then left).
+   <- callers reading physics.data.site("eer_site_pos").xpos / .xmat (examples/2_synthetic_data.py:34, env_sim.py:62-64). */
+int km_site_poses(km_handle h, void* xpos_dev, void* xmat_dev, void* stream);
+int km_n_arm(km_handle h);
 
 /* Diagnostics of the most recent step's last sub-step: [n] Newton iterations, [n] line-search evaluations (cumulative). */
 int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream);

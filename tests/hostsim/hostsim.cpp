@@ -42,6 +42,7 @@ template <class S, typename T> struct HostSim : HostSimBase {
     for (int i = 0; i < D::NV; i++) e.warm[i] = (T)r[k++];
     for (int i = 0; i < D::NMOCAP * 7; i++) e.mocap[i] = (T)r[k++];
     e.time = (T)r[k++];
+    for (int i = 0; i < 3; i++) e.cube_lo[i] = (T)r[k++];
     e.step = step; e.episode = episode;
   }
   void get_state(double* r, int* step, int* episode) override {
@@ -52,6 +53,7 @@ template <class S, typename T> struct HostSim : HostSimBase {
     for (int i = 0; i < D::NV; i++) r[k++] = (double)e.warm[i];
     for (int i = 0; i < D::NMOCAP * 7; i++) r[k++] = (double)e.mocap[i];
     r[k++] = (double)e.time;
+    for (int i = 0; i < 3; i++) r[k++] = (double)e.cube_lo[i];
     if (step) *step = e.step;
     if (episode) *episode = e.episode;
   }

@@ -61,7 +61,7 @@ class HostSim:
         d = (C.c_int * 8)()
         self.L.hs_dims(self.h, d)
         self.nq, self.nv, self.nu, self.nmocap, self.obs_dim, self.act_dim, self.maxcon = list(d)[:7]
-        self.state_dim = self.nq + 2 * self.nv + self.nu + 7 * self.nmocap + 1
+        self.state_dim = self.nq + 2 * self.nv + self.nu + 7 * self.nmocap + 1 + 3
 
     def __del__(self):
         try:
@@ -70,7 +70,8 @@ class HostSim:
             pass
 
     def pack(self, st):
-        return np.concatenate([st["qpos"], st["qvel"], st["ctrl"], st["warm"], st["mocap"], [st["time"]]]).astype(np.float64)
+        return np.concatenate([st["qpos"], st["qvel"], st["ctrl"], st["warm"], st["mocap"], [st["time"]],
+                               st.get("cube_lo", np.zeros(3))]).astype(np.float64)
 
     def unpack(self, rec):
         o = 0
@@ -79,6 +80,8 @@ class HostSim:
             out[k] = rec[o:o + n].copy()
             o += n
         out["time"] = float(rec[o])
+        out["cube_lo"] = rec[o + 1:o + 4].copy()
+        out["qpos"][-7:-4] += out["cube_lo"]      # the cube's position is hi + lo (fp32 build; lo = 0 in fp64)
         return out
 
     def set_state(self, st, step=0, episode=0):

@@ -1,0 +1,126 @@
+"""GPU: the reference-facing Python API (KManipEnv / make, KManipVectorEnv) and size-independent properties of the
+CUDA path at BASELINE.json's batch sizes.  The API checks restate what gymnasium's check_env pins for the reference
+(tests/test_env.py:8-24: spaces, dtypes, bounds, 5-tuple types), plus the TimeLimit truncation of gym.make."""
+import numpy as np
+import pytest
+
+import gym_kmanip_b200 as k
+
+STATE_IDS = ["KManipSoloArm", "KManipSoloArmQPos", "KManipDualArm", "KManipDualArmQPos", "KManipTorso"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", STATE_IDS)
+def test_single_env_follows_the_reference_contract(env_id):
+    env = k.make(env_id)
+    u = env.unwrapped
+    obs, info = env.reset(seed=0)
+    assert list(obs) == ["q_pos", "q_vel", "cube_pos", "cube_orn"]
+    assert u.observation_space.contains(obs), obs
+    for key in ("step", "episode", "is_success", "q_keys", "q_len", "a_len", "obs_list", "act_list", "cameras", "sim",
+                "sim_time", "cpu_time", "reward", "terminated"):
+        assert key in info
+    assert info["episode"] == 1 and info["step"] == 0 and info["reward"] is None and info["sim_time"] == 0.0
+    home = k.ENV_REGISTRY[env_id]["q_pos_home"]
+    qpos0 = u.env.physics.data.qpos
+    assert np.allclose(qpos0[: u.q_len], home.astype(np.float64)) and np.allclose(qpos0[-4:], [1, 0, 0, 0])
+    assert 0.1 <= qpos0[-7] <= 0.3 and 0.5 <= qpos0[-6] <= 0.7 and 0.6 <= qpos0[-5] <= 0.7      # CUBE_SPAWN_RANGE
+    u.action_space.seed(0)
+    for t in range(k.MAX_EPISODE_STEPS):
+        a = u.action_space.sample()
+        obs, reward, terminated, truncated, info = env.step(a)
+        assert u.observation_space.contains(obs)
+        assert all(v.dtype == np.float64 for v in obs.values())
+        assert isinstance(reward, float) and np.isfinite(reward)
+        assert terminated is False and isinstance(truncated, bool)
+        assert truncated == (t == k.MAX_EPISODE_STEPS - 1)           # TimeLimit of gym.make (__init__.py:28,247)
+        assert info["step"] == t + 1 and info["is_success"] == (reward > 2.0)
+        assert abs(info["sim_time"] - 0.02 * (t + 1)) < 1e-9          # 10 sub-steps of 2 ms per env step
+    d = u.env.physics.data
+    assert d.qpos.shape == (u.env.physics.model.nq,) and d.qvel.shape == (u.env.physics.model.nv,)
+    assert abs(np.linalg.norm(d.qpos[-4:]) - 1) < 1e-9
+    site = d.site("eer_site_pos")
+    assert site.xpos.shape == (3,) and site.xmat.shape == (9,)
+    if "eer_pos" in u.act_list:   # the mocap body carries the last IK goal (env_sim.py:67-70)
+        assert np.linalg.norm(d.mocap_pos[0] - site.xpos) < 0.1
+    obs2, info2 = env.reset()
+    assert info2["episode"] == 2 and info2["step"] == 0
+    env.close()
+
+
+@pytest.mark.gpu
+def test_single_env_matches_oracle_free_running():
+    """The single-env class end to end (dict actions in, dict observations out) against the oracle driven the same
+    way, free-running over one episode from the same spawn (fp64: agreement stays far below contact chaos)."""
+    from oracle import oracle as om
+    env = k.make("KManipSoloArm")
+    o = om.Oracle("KManipSoloArm")
+    xyz = np.array([0.22, 0.61, 0.63])
+    obs, _ = env.reset(options={"cube_xyz": xyz})
+    assert np.allclose(np.concatenate(list(obs.values())), o.reset(xyz), atol=1e-12)
+    rng = np.random.default_rng(1)
+    for t in range(20):
+        a = rng.uniform(-1, 1, 7).astype(np.float32)
+        obs, rew, _, _, _ = env.step({"eer_pos": a[0:3], "eer_orn": a[3:6], "grip_r": a[6:7]})
+        o_obs, o_rew = o.step(a)
+        assert np.abs(np.concatenate(list(obs.values())) - o_obs).max() < 1e-7 and abs(rew - o_rew) < 1e-7
+    env.close()
+
+
+@pytest.mark.gpu
+def test_vector_env_autoreset_and_totals():
+    import torch
+    n = 512
+    env = k.make_vec("KManipDualArm", n, dtype="float32", seed=5)
+    obs, _ = env.reset()
+    assert list(obs) == ["q_pos", "q_vel", "cube_pos", "cube_orn"] and obs["q_pos"].shape == (n, 20) and obs["cube_orn"].shape == (n, 4)
+    first = {kk: v.clone() for kk, v in obs.items()}
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(k.MAX_EPISODE_STEPS + 2):
+        flat = env.sample_actions(gen)
+        act = {kk: flat[:, sl] for kk, sl in env.action_layout.items()}       # dict actions with the reference keys
+        obs, rew, term, trunc, info = env.step(act)
+        assert not term.any()
+        assert bool(trunc.all()) == (t == k.MAX_EPISODE_STEPS - 1) and bool(trunc.any()) == (t == k.MAX_EPISODE_STEPS - 1)
+        for v in obs.values():
+            assert float(v.min()) >= -1 and float(v.max()) <= 1
+        if t == k.MAX_EPISODE_STEPS - 1:
+            # same-step autoreset: obs is the first observation of the new episode, final_obs the last of the old one
+            assert torch.equal(obs["q_pos"], first["q_pos"]) and torch.equal(obs["q_vel"], first["q_vel"])
+            assert not torch.equal(obs["cube_pos"], first["cube_pos"])       # new spawn for episode 1
+            assert not torch.equal(info["final_obs"]["q_pos"], first["q_pos"])
+            assert (info["final_return"] != 0).all()
+    tot = env.totals.cpu().numpy()
+    assert tot[1] == n * (k.MAX_EPISODE_STEPS + 2) and tot[2] == n
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id,n", [("KManipSoloArmQPos", 4096), ("KManipSoloArm", 8192)])
+def test_properties_at_baseline_batch_sizes(env_id, n):
+    """Size-independent properties at the BASELINE.json batch sizes: bit-exact determinism, independence from how envs
+    are sharded into handles (global env ids), unit quaternions, observation bounds, truncation every 64 steps."""
+    import torch
+    from gym_kmanip_b200.batch_sim import BatchSim
+    whole = BatchSim(env_id, n, dtype="float32", seed=9)
+    again = BatchSim(env_id, n, dtype="float32", seed=9)
+    half = [BatchSim(env_id, n // 2, dtype="float32", seed=9, env0=0), BatchSim(env_id, n // 2, dtype="float32", seed=9, env0=n // 2)]
+    for s in [whole, again] + half:
+        s.reset()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    ntrunc = 0
+    for t in range(70):
+        act = torch.rand(n, whole.act_dim, device="cuda", generator=gen) * 2 - 1
+        obs, rew, term, trunc = whole.step(act, autoreset=True)
+        obs2, rew2, _, _ = again.step(act, autoreset=True)
+        assert torch.equal(obs, obs2) and torch.equal(rew, rew2)
+        oh = torch.cat([half[0].step(act[: n // 2].contiguous(), autoreset=True)[0], half[1].step(act[n // 2:].contiguous(), autoreset=True)[0]])
+        assert torch.equal(obs, oh)
+        ntrunc += int(trunc.sum())
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert float(obs.min()) >= -1 and float(obs.max()) <= 1
+        quat = obs[:, -4:]
+        assert float((quat.norm(dim=1) - 1).abs().max()) < 1e-5
+    assert ntrunc == n
+    for s in [whole, again] + half:
+        s.close()
