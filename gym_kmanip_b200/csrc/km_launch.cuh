@@ -198,12 +198,16 @@ template <class S, typename T> struct Launch {
   static cudaError_t reset(const KmArgs& a) { return dispatch(1, a); }
   static cudaError_t contacts(const KmArgs& a) { return dispatch(2, a); }
   template <int G> static cudaError_t prep(int epb, int* ctas) {
-    const size_t sm = smem_bytes<S, T>(epb);
+    // the attribute is per function, not per handle: always opt in to the device maximum so that handles with
+    // different envs-per-CTA can coexist in one process
+    int dev = 0, optin = 0;
     cudaError_t err;
-    if ((err = cudaFuncSetAttribute(k_env_step<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(k_reset<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(k_contacts<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, sm);
+    if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+    if ((err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_env_step<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_reset<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_contacts<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, smem_bytes<S, T>(epb));
   }
   static cudaError_t prepare(int G, int epb, int* ctas) {
     if (G == 32) return prep<32>(epb, ctas);

@@ -123,6 +123,7 @@ struct ko_data {
   real qM[NV][NV], qLD[NV][NV], qLDiagInv[NV];
   real actuator_length[NU];
   int ncon;
+  int ncon_peak;   /* test diagnostic: most contacts seen by any collision pass since the caller cleared it */
   ko_contact contact[MAXCON];
   int nefc;
   int efc_type[MAXEFC], efc_id[MAXEFC];
@@ -537,6 +538,7 @@ static void ko_collision(const ko_model* m, ko_data* d) {
     if (t1 == KO_GEOM_PLANE && t2 == KO_GEOM_BOX) ko_plane_box(m, d, p);
     else if (t1 == KO_GEOM_SPHERE && t2 == KO_GEOM_BOX) ko_sphere_box(m, d, p);
   }
+  if (d->ncon > d->ncon_peak) d->ncon_peak = d->ncon;
 }
 
 /* ------------------------------------------------------------------------------------------- Jacobians */
@@ -1469,7 +1471,8 @@ int ko_get_field(const ko_model* m, const void* dv, const char* name, double* ou
 int ko_batch_step(const ko_model* m, const ko_task* t, int n, double* qpos, double* qvel, double* ctrl, double* warm,
                   double* time, int* step_count, int* episode, double* mocap, const float* action, double* obs,
                   double* final_obs, double* reward, unsigned char* truncated, int* con_flags, int* ncon,
-                  int* con_geoms /* [n][2*MAXCON] */, int autoreset, unsigned long long seed, unsigned long long env0, int nthreads) {
+                  int* con_geoms /* [n][2*MAXCON] */, int autoreset, unsigned long long seed, unsigned long long env0, int nthreads,
+                  int* ncon_peak /* optional [n]: most contacts in any collision pass of the step, incl. the opening one */) {
   int od = ko_obs_dim(t);
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -1482,12 +1485,14 @@ int ko_batch_step(const ko_model* m, const ko_task* t, int n, double* qpos, doub
     for (int e = 0; e < n; e++) {
       load_state(m, d, qpos + (size_t)e * m->nq, qvel + (size_t)e * m->nv, ctrl + (size_t)e * m->nu, warm + (size_t)e * m->nv,
                  time[e], mocap ? mocap + (size_t)e * 7 * m->nmocap : 0);
+      d->ncon_peak = 0;
       ko_step1(m, d);
       ko_env_step_(m, d, t, action + (size_t)e * t->act_dim, 0, 0);
       int fl;
       reward[e] = ko_reward(m, d, t, &fl);
       if (con_flags) con_flags[e] = fl;
       if (ncon) ncon[e] = d->ncon;
+      if (ncon_peak) ncon_peak[e] = d->ncon_peak;
       if (con_geoms) for (int c = 0; c < MAXCON; c++) {
         con_geoms[(size_t)e * 2 * MAXCON + 2 * c] = c < d->ncon ? d->contact[c].geom1 : -1;
         con_geoms[(size_t)e * 2 * MAXCON + 2 * c + 1] = c < d->ncon ? d->contact[c].geom2 : -1;

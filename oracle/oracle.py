@@ -202,9 +202,10 @@ class Oracle:
 
 
 def batch_step(orc: Oracle, state: Dict[str, np.ndarray], action: np.ndarray, autoreset: bool = True, seed: int = 0,
-               env0: int = 0, nthreads: int = 0):
+               env0: int = 0, nthreads: int = 0, ncon_peak: Optional[np.ndarray] = None):
     """Advance a batch of envs one env-step on the CPU (in place on `state`); returns obs, final_obs, reward,
-    truncated, flags, ncon, contact geom pairs."""
+    truncated, flags, ncon, contact geom pairs.  ncon_peak (optional int32 [n]) receives the most contacts any of the
+    step's collision passes saw (a test diagnostic: was the cube touching anything at any sub-step)."""
     n = state["qpos"].shape[0]
     L = orc.L
     od = orc.obs_dim
@@ -219,7 +220,7 @@ def batch_step(orc: Oracle, state: Dict[str, np.ndarray], action: np.ndarray, au
                     _dp(state["warm"]), _dp(state["time"]), ip(state["step"]), ip(state["episode"]), _dp(state["mocap"]),
                     a.ctypes.data_as(C.POINTER(C.c_float)), _dp(obs), _dp(fobs), _dp(rew),
                     trunc.ctypes.data_as(C.POINTER(C.c_ubyte)), ip(flags), ip(ncon), ip(geoms), C.c_int(int(autoreset)),
-                    C.c_ulonglong(seed), C.c_ulonglong(env0), C.c_int(nthreads))
+                    C.c_ulonglong(seed), C.c_ulonglong(env0), C.c_int(nthreads), None if ncon_peak is None else ip(ncon_peak))
     return obs, fobs, rew, trunc, flags, ncon, geoms
 
 

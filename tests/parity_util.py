@@ -37,16 +37,16 @@ def oracle_rollout(env_id, n, steps, seed=0, action_seed=1, nthreads=0, round32=
         st["mocap"] = np.zeros((n, 0))
     rng = np.random.default_rng(action_seed)
     out = []
-    ncon_prev = np.zeros(n, dtype=np.int32)
     for _ in range(steps):
         a = rng.uniform(-1, 1, (n, o.task.act_dim)).astype(np.float32)
         if round32:
             for k in _REAL_FIELDS:
                 st[k][...] = st[k].astype(np.float32).astype(np.float64)
         before = {k: v.copy() for k, v in st.items()}
-        obs, fobs, rew, trunc, flags, ncon, geoms = orc_mod.batch_step(o, st, a, autoreset=True, seed=seed, nthreads=nthreads)
+        peak = np.zeros(n, dtype=np.int32)
+        obs, fobs, rew, trunc, flags, ncon, geoms = orc_mod.batch_step(o, st, a, autoreset=True, seed=seed, nthreads=nthreads,
+                                                                       ncon_peak=peak)
         after = {k: v.copy() for k, v in st.items()}
         out.append(dict(before=before, action=a, obs=obs, final_obs=fobs, reward=rew, truncated=trunc, flags=flags, ncon=ncon,
-                        geoms=geoms, after=after, ncon_before=ncon_prev))
-        ncon_prev = np.where(trunc != 0, 0, ncon).astype(np.int32)
+                        geoms=geoms, after=after, ncon_peak=peak))
     return o, out

@@ -5,7 +5,7 @@ Tolerances (parity_util.rel_err: max |a - b| over a batch field / that field's o
               scale is 1 while its q_vel entries carry the absolute error of velocities of magnitude ~30 rad/s;
               contact-pair indices, contact counts and done flags bit-exact for every env.
   fp32 build: teacher states are float32-representable (oracle_rollout(round32=True)), so no input-rounding error
-              enters.  Envs whose cube touches nothing: 2e-5 on positions / 2e-5 on velocities relative to the batch
+              enters.  Envs whose cube touches nothing: 2e-5 on positions / 1e-4 on velocities (1e-3 absolute on the observation record) relative to the batch
               magnitude (~100 rad/s) -- the north_star 1e-5 figure is per physics sub-step, an env step chains ten.
               Envs in contact: absolute bounds CONTACT_TOL_*_F32 (parity_util; DESIGN.md "fp32 and the cube"), and
               bit-exact contact indices except where the oracle itself changes its answer under a one-ulp change of
@@ -50,7 +50,7 @@ def _run(env_id, dtype, n, steps, tol_pos, tol_vel, tol_obs):
         g = _sim_state(sim)
         a = rec["after"]
         obs_n, rew_n = obs.double().cpu().numpy(), rew.double().cpu().numpy()
-        touch = ((rec["ncon"] > 0) | (rec["ncon_before"] > 0)) if f32 else np.zeros(n, dtype=bool)
+        touch = (rec["ncon_peak"] > 0) if f32 else np.zeros(n, dtype=bool)
         free = ~touch
         n_touch += int(touch.sum())
         if free.any():
@@ -93,7 +93,7 @@ def test_env_step_parity_fp64(env_id):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env_id", ENVS)
 def test_env_step_parity_fp32(env_id):
-    _run(env_id, "float32", n=64, steps=70, tol_pos=2e-5, tol_vel=2e-5, tol_obs=2e-4)
+    _run(env_id, "float32", n=64, steps=70, tol_pos=2e-5, tol_vel=1e-4, tol_obs=1e-3)
 
 
 @pytest.mark.gpu

@@ -65,7 +65,7 @@ def test_env_step_matches_oracle(env_id, dtype, tol_pos, tol_vel):
             ep = max(rel_err(a["qpos"], rec["after"]["qpos"][i]), rel_err(a["ctrl"], rec["after"]["ctrl"][i]))
             ev = rel_err(a["qvel"], rec["after"]["qvel"][i], floor=1.0)
             eo = max(rel_err(out["obs"], rec["obs"][i], floor=1.0), rel_err(out["reward"], rec["reward"][i], floor=1.0))
-            touching = dtype == 32 and (rec["ncon"][i] > 0 or rec["ncon_before"][i] > 0)
+            touching = dtype == 32 and rec["ncon_peak"][i] > 0
             if touching:
                 worst["cpos"], worst["cvel"] = max(worst["cpos"], ep, eo), max(worst["cvel"], ev)
             else:
