@@ -34,7 +34,7 @@ UNIT = "env-steps/s"
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=128)
+    p.add_argument("--steps", type=int, default=512)
     p.add_argument("--warmup", type=int, default=8)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--env", default="KManipSoloArmQPos")
@@ -240,10 +240,18 @@ def run_ours(a):
         fl = flops.get(a.env)
         fp32 = None
         if fl:
-            fp_peak = flops.get("fp32_peak_tflops", 74.4) if sim.tdtype == torch.float32 else flops.get("fp64_peak_tflops", 37.2)
+            # denominator: FMA throughput of the CUDA-core pipe measured on this GPU right now (km_measure_fma_peak)
+            import ctypes as C
+            from gym_kmanip_b200 import _lib
+            pk = C.c_double(0)
+            f32 = sim.tdtype == torch.float32
+            rc = _lib.load().km_measure_fma_peak(local, 32 if f32 else 64, C.byref(pk))
+            fp_peak, src = (pk.value, "measured (km_measure_fma_peak, dependent-FMA chains, this run)") if rc == 0 and pk.value > 0 else \
+                ((74.4 if f32 else 37.2), "nominal 148 SM x 128 lanes x 2 x 1.965 GHz")
             ach = fl * n / (ms_per_step * 1e-3) / 1e12
-            fp32 = {"bound": "fp32" if sim.tdtype == torch.float32 else "fp64", "achieved": ach, "peak": fp_peak, "unit": "TFLOP/s",
-                    "frac": ach / fp_peak, "flop_per_env_step": fl, "peak_source": flops.get("peak_source", "nominal 148 SM x 128 lanes x 2 x 1.965 GHz")}
+            fp32 = {"bound": "fp32" if f32 else "fp64", "achieved": ach, "peak": fp_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp_peak, "flop_per_env_step": fl, "peak_source": src,
+                    "flop_source": "counted by the oracle's operation-counting build (profiles/flops_per_env_step.json)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -255,7 +263,7 @@ def run_ours(a):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": flops.get("dram_traffic_bytes_per_launch"), "peak_source": peak_src,
+                         "traffic": flops.get("dram_traffic_bytes_per_launch", {}).get(f"{a.env}:{n}:{cfg['lanes_per_env']}"), "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": alg_bytes,
                          "note": "the path is FP-pipe/latency bound by construction (SURVEY.md 8d); see roofline_fp"},
             "roofline_fp": fp32,

@@ -9,12 +9,12 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkmanip_b200.so")
+LIB_PATH = os.environ.get("KMANIP_B200_LIB") or os.path.join(_HERE, "lib", "libkmanip_b200.so")   # env override: A/B experiments
 CSRC = os.path.join(_HERE, "csrc")
 _LIB = None
 
 EXPORTS = [
-    "km_last_error", "km_version", "km_create", "km_destroy", "km_nq", "km_nv", "km_nu", "km_nmocap", "km_obs_dim",
+    "km_last_error", "km_version", "km_measure_fma_peak", "km_create", "km_destroy", "km_nq", "km_nv", "km_nu", "km_nmocap", "km_obs_dim",
     "km_act_dim", "km_state_dim", "km_max_contacts", "km_num_envs", "km_dtype", "km_configure", "km_launch_count",
     "km_launch_config", "km_reset", "km_step", "km_get_state", "km_set_state", "km_state_ptr", "km_contacts",
     "km_solver_stats", "km_site_poses", "km_n_arm", "km_reset_host", "km_step_host",
@@ -47,6 +47,7 @@ def load() -> C.CDLL:
     vp, ip, u64 = C.c_void_p, C.c_int, C.c_uint64
     L.km_last_error.restype = C.c_char_p
     L.km_version.restype = C.c_char_p
+    L.km_measure_fma_peak.argtypes = [ip, ip, C.POINTER(C.c_double)]
     L.km_create.argtypes = [vp, vp, ip, ip, ip, ip, u64, u64, C.POINTER(vp)]
     L.km_destroy.argtypes = [vp]
     L.km_destroy.restype = None

@@ -54,7 +54,24 @@ struct DeviceGuard {
 
 static int configure(km_sim* h, int G, int epb) {
   if (G == 0) G = h->G;
-  if ((G != 16 && G != 32) || G < h->vt.nlanes_min) return fail(KM_ERR_ARG, "lanes_per_env must be 16 or 32 and at least the number of dofs");
+  if (G == 1) {   // thread-per-env: epb = envs (threads) per CTA, bounded by the shared memory one CTA can hold
+    const int cap = h->vt.tpe_max_envs;
+    if (cap < 1) return fail(KM_ERR_ARG, "an env does not fit in shared memory");
+    if (epb == 0) {   // balance the waves over the SMs (4096 envs on 148 SMs -> 28 envs per CTA, one wave)
+      const long per_wave = (long)h->num_sms * cap, waves = ((long)h->n + per_wave - 1) / per_wave;
+      epb = (int)(((long)h->n + h->num_sms * waves - 1) / (h->num_sms * waves));
+      if (epb > cap) epb = cap;
+    }
+    if (epb < 1 || epb > cap) return fail(KM_ERR_ARG, "envs_per_block out of range for thread-per-env CTAs");
+    int ctas = 0;
+    KM_CUDA(h->vt.prepare(1, epb, &ctas));
+    if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
+    h->G = 1; h->epb = epb; h->ctas_per_sm = ctas;
+    const long tiles = ((long)h->n + epb - 1) / epb, resident = (long)h->num_sms * ctas;
+    h->grid = (int)(tiles < resident ? tiles : resident);
+    return KM_OK;
+  }
+  if ((G != 16 && G != 32) || G < h->vt.nlanes_min) return fail(KM_ERR_ARG, "lanes_per_env must be 1, 16 or 32 and (for 16 / 32) at least the number of dofs");
   int dev_smem = 0;
   KM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   const size_t model_b = (h->vt.model_bytes + 15) / 16 * 16;
@@ -92,7 +109,50 @@ static KmArgs base_args(km_sim* h, void* stream) {
   return a;
 }
 
+// FMA-pipe micro-benchmark: 8 independent dependent-FMA chains per thread, enough threads to fill every SM
+template <typename T> __global__ void k_fma_peak(T* out, int iters) {
+  T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const T b = (T)0.999, c = (T)1e-4;
+  for (int i = 0; i < iters; i++) {
+    a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+    a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+template <typename T> static int measure_fma(int device, double* tflops) {
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(KM_ERR_CUDA, "cudaSetDevice failed");
+  int sms = 0;
+  KM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int threads = 1024, blocks = sms * 2, iters = 1 << 16;
+  T* out = nullptr;
+  KM_CUDA(cudaMalloc((void**)&out, (size_t)threads * blocks * sizeof(T)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    k_fma_peak<T><<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * threads * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  KM_CUDA(cudaGetLastError());
+  *tflops = best;
+  return KM_OK;
+}
+
 extern "C" {
+
+int km_measure_fma_peak(int device, int dtype, double* tflops) {
+  if (!tflops) return fail(KM_ERR_ARG, "null output");
+  return dtype == KM_F64 ? measure_fma<double>(device, tflops) : measure_fma<float>(device, tflops);
+}
 
 const char* km_last_error(void) { return g_err.c_str(); }
 const char* km_version(void) { return "kmanip_b200 0.1 (sm_100a)"; }
@@ -190,7 +250,7 @@ int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* 
   if (envs_per_block) *envs_per_block = h->epb;
   if (grid) *grid = h->grid;
   if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
-  if (smem_bytes) *smem_bytes = (int)((h->vt.model_bytes + 15) / 16 * 16 + (size_t)h->epb * h->vt.env_bytes);
+  if (smem_bytes) *smem_bytes = (int)((h->vt.model_bytes + 15) / 16 * 16 + (size_t)h->epb * (h->G == 1 ? h->vt.tpe_env_bytes : h->vt.env_bytes));
   return KM_OK;
 }
 

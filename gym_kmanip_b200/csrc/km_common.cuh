@@ -101,13 +101,16 @@ template <int G> struct Grp {
   // halving the issue efficiency of everything that follows; converge() is placed after such loops.
   // a whole-warp group names its lanes with a literal mask: the compiler then emits bare SHFL / no WARPSYNC
   KM_HD unsigned lanes() const { return G == 32 ? 0xffffffffu : mask; }
+  // G == 1 is the thread-per-env mapping: every thread owns an env, so all group collectives are identities and
+  // nothing may synchronise with other threads (their control flow is independent).
   KM_HD void converge() const {
 #if defined(__CUDA_ARCH__)
-    if (G < 32) __syncwarp(wmask);
+    if (G > 1 && G < 32) __syncwarp(wmask);
 #endif
   }
   template <typename T> KM_HD T shfl(T v, int src) const {
 #if defined(__CUDA_ARCH__)
+    if (G == 1) return v;
     return __shfl_sync(lanes(), v, src, G);
 #else
     return v;
@@ -117,13 +120,19 @@ template <int G> struct Grp {
   // sub-step together makes the warps of an SM fetch the same instructions at the same time: the hot loop is far
   // larger than the 32 KB L1.5 instruction cache, and unaligned warps spent over half their stall time waiting for
   // instruction fetch.  Only called from code every thread of the CTA executes the same number of times.
+  // KM_LOCKSTEP: 2 = phases and Newton iterations CTA-wide, 1 = phases only, 0 = warps run free
+#ifndef KM_LOCKSTEP
+#define KM_LOCKSTEP 2
+#endif
   KM_HD void cta_sync() const {
 #if defined(__CUDA_ARCH__)
-    __syncthreads();
+    if (G > 1 && KM_LOCKSTEP >= 1) __syncthreads();
 #endif
   }
   KM_HD bool cta_any(bool p) const {
 #if defined(__CUDA_ARCH__)
+    if (G == 1) return p;
+    if (KM_LOCKSTEP < 2) return (__ballot_sync(0xffffffffu, p) != 0u);
     return __syncthreads_or(p) != 0;
 #else
     return p;
@@ -131,7 +140,7 @@ template <int G> struct Grp {
   }
   KM_HD void sync() const {
 #if defined(__CUDA_ARCH__)
-    __syncwarp(lanes());
+    if (G > 1) __syncwarp(lanes());
 #endif
   }
   template <typename T> KM_HD T sum(T v) const {
@@ -143,6 +152,7 @@ template <int G> struct Grp {
   }
   KM_HD bool any(bool p) const {
 #if defined(__CUDA_ARCH__)
+    if (G == 1) return p;
     return (__ballot_sync(lanes(), p) & lanes()) != 0u;
 #else
     return p;

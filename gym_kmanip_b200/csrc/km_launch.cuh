@@ -39,8 +39,8 @@ struct KmArgs {
 };
 
 struct KmVtable {
-  size_t model_bytes, env_bytes, scalar_bytes;
-  int nq, nv, nu, nmocap, obs_dim, state_dim, maxcon, nlanes_min, max_threads;
+  size_t model_bytes, env_bytes, scalar_bytes, tpe_env_bytes;
+  int nq, nv, nu, nmocap, obs_dim, state_dim, maxcon, nlanes_min, max_threads, tpe_max_envs;
   int (*fill)(const km_model*, const km_task*, void* dst, std::string& err);
   cudaError_t (*step)(const KmArgs&);
   cudaError_t (*reset)(const KmArgs&);
@@ -78,9 +78,8 @@ template <class S, typename T> __device__ __forceinline__ const Model<S, T>& sta
 }
 
 // state record <-> the leading members of Env (qpos, qvel, ctrl, warm, mocap, time, cube_lo are laid out contiguously)
-template <class S, typename T, int G> __device__ __forceinline__ void load_state(Env<S, T>& e, const KmArgs& a, long env, const Grp<G>& g) {
+template <class S, typename T, int G, class E_> __device__ __forceinline__ void load_state(E_& e, const KmArgs& a, long env, const Grp<G>& g) {
   constexpr int SD = Dim<S>::STATE;
-  typedef Env<S, T> E_;
   static_assert(offsetof(E_, time) == (SD - 4) * sizeof(T) && offsetof(E_, cube_lo) == (SD - 3) * sizeof(T), "state members of Env must be contiguous");
   const T* src = (const T*)a.state + env * SD;
   T* dst = (T*)&e;
@@ -88,7 +87,7 @@ template <class S, typename T, int G> __device__ __forceinline__ void load_state
   if (g.lane == 0) { e.step = a.step[env]; e.episode = a.episode[env]; }
   g.sync();
 }
-template <class S, typename T, int G> __device__ __forceinline__ void store_state(const Env<S, T>& e, const KmArgs& a, long env, const Grp<G>& g) {
+template <class S, typename T, int G, class E_> __device__ __forceinline__ void store_state(const E_& e, const KmArgs& a, long env, const Grp<G>& g) {
   constexpr int SD = Dim<S>::STATE;
   T* dst = (T*)a.state + env * SD;
   const T* src = (const T*)&e;
@@ -125,6 +124,46 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
       }
     }
     g.sync();
+  }
+}
+
+// Thread-per-env mapping (G = 1): every thread owns one env; its working set is one contiguous record in shared
+// memory with an odd word stride (conflict-free across lanes, see Env), the model tables sit in front of the records.
+template <class S, typename T> struct Tpe {
+  typedef Env<S, T, true> E;
+  static constexpr size_t unit = sizeof(T) == 4 ? 4 : 8;
+  static constexpr size_t words = (sizeof(E) + unit - 1) / unit;
+  static constexpr size_t stride = (words | 1) * unit;                 // odd number of bank units per record
+  static constexpr int max_envs() {
+    const int fit = (int)((232448 - model_smem<S, T>()) / stride);
+    return fit > 128 ? 128 : fit;
+  }
+  static constexpr int threads() { return (max_envs() + 31) / 32 * 32; }
+  static size_t smem(int epb) { return model_smem<S, T>() + (size_t)epb * stride; }
+};
+template <class S, typename T> __global__ void __launch_bounds__(Tpe<S, T>::threads()) k_env_step_tpe(KmArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  typedef typename Tpe<S, T>::E E;
+  const Model<S, T>& m = stage_model<S, T>(smem, a.model);
+  Grp<1> g;
+  g.lane = 0; g.mask = 1u; g.wmask = 1u;
+  if ((int)threadIdx.x >= a.epb) return;          // a CTA may hold fewer envs than its rounded-up warp
+  E& e = *(E*)(smem + model_smem<S, T>() + (size_t)threadIdx.x * Tpe<S, T>::stride);
+  init_env<S, T, 1>(e, m, g);
+  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON};
+  for (long env = (long)blockIdx.x * a.epb + threadIdx.x; env < a.n; env += (long)gridDim.x * a.epb) {
+    load_state<S, T, 1>(e, a, env, g);
+#ifdef KM_TPE_DEBUG
+    const long long t0 = clock64();
+    e.solver_niter = 0;
+#endif
+    env_step<S, T, 1>(e, m, g, a.act + env * m.act_dim, o, env, a.autoreset, a.seed, a.env0);
+    store_state<S, T, 1>(e, a, env, g);
+    if (a.niter) a.niter[env] = e.solver_niter;
+    if (a.ls) a.ls[env] = e.ls_evals;
+#ifdef KM_TPE_DEBUG
+    if (a.ls) a.ls[env] = (int)((clock64() - t0) >> 10);   // debug build: kilo-cycles of this thread's env step
+#endif
   }
 }
 
@@ -190,6 +229,15 @@ template <class S, typename T> struct Launch {
     return cudaGetLastError();
   }
   static cudaError_t dispatch(int which, const KmArgs& a) {
+    if (a.G == 1 && which == 0) {
+      k_env_step_tpe<S, T><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), Tpe<S, T>::smem(a.epb), a.stream>>>(a);
+      return cudaGetLastError();
+    }
+    if (a.G == 1) {   // reset / contacts are not hot: one env per warp with a small CTA
+      KmArgs b = a;
+      b.G = 32; b.epb = 4; b.grid = (a.n + 3) / 4 < 148 * 8 ? (a.n + 3) / 4 : 148 * 8;
+      return run<32>(which, b);
+    }
     if (a.G == 32) return run<32>(which, a);
     if constexpr (D::NV <= 16) { if (a.G == 16) return run<16>(which, a); }
     return cudaErrorInvalidValue;
@@ -210,6 +258,15 @@ template <class S, typename T> struct Launch {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, smem_bytes<S, T>(epb));
   }
   static cudaError_t prepare(int G, int epb, int* ctas) {
+    if (G == 1) {
+      cudaError_t err = prep<32>(4, ctas);
+      if (err != cudaSuccess) return err;
+      int dev = 0, optin = 0;
+      if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
+      if ((err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
+      if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T>, (epb + 31) / 32 * 32, Tpe<S, T>::smem(epb));
+    }
     if (G == 32) return prep<32>(epb, ctas);
     if constexpr (D::NV <= 16) { if (G == 16) return prep<16>(epb, ctas); }
     return cudaErrorInvalidValue;
@@ -221,7 +278,7 @@ template <class S, typename T> struct Launch {
     KmVtable v;
     v.model_bytes = sizeof(Model<S, T>); v.env_bytes = env_smem<S, T>(); v.scalar_bytes = sizeof(T);
     v.nq = D::NQ; v.nv = D::NV; v.nu = D::NU; v.nmocap = D::NMOCAP; v.obs_dim = D::OBS;
-    v.state_dim = D::STATE; v.maxcon = D::MAXCON; v.nlanes_min = D::NV <= 16 ? 16 : 32; v.max_threads = max_threads<S, T>();
+    v.state_dim = D::STATE; v.maxcon = D::MAXCON; v.nlanes_min = D::NV <= 16 ? 16 : 32; v.max_threads = max_threads<S, T>(); v.tpe_max_envs = Tpe<S, T>::max_envs(); v.tpe_env_bytes = Tpe<S, T>::stride;
     v.fill = &fill; v.step = &step; v.reset = &reset; v.contacts = &contacts; v.prepare = &prepare;
     return v;
   }

@@ -95,8 +95,13 @@ template <class S, typename T> struct Model {
 };
 
 // -------------------------------------------------------------------------------------------- working set
-template <class S, typename T> struct Env {
+struct EmptyStage {};
+// TPE = thread-per-env working set: one contiguous record per thread in shared memory whose size in words is odd
+// (lane t's field i sits in bank (t * words + i) mod 32, so equal fields of the 32 lanes never conflict).  It must not
+// contain 8-byte members when T is float (odd strides break their alignment): the fp64 IK scratch is left out.
+template <class S, typename T, bool TPE_ = false> struct Env {
   typedef Dim<S> D;
+  static constexpr bool TPE = TPE_;
   // persistent state (what km_get_state / km_set_state expose)
   T qpos[D::NQ], qvel[D::NV], ctrl[D::NU], warm[D::NV], mocap[D::NMOCAP * 7], time;
   // low-order part of the cube's position: qpos[NVA..NVA+2] + cube_lo is the position.  The cube rests ~1e-7 m deep in
@@ -145,12 +150,22 @@ template <class S, typename T> struct Env {
     T Ma[D::NV], grad[D::NV], Mgrad[D::NV], search[D::NV], Mv[D::NV], qfc[D::NV], hdiag[D::NV];
     T H[D::NV][D::HS], Hd[D::NV];
   };
+  struct StageT {   // Newton solver of the thread-per-env mapping (km_solver_tpe.cuh)
+    T Ma[D::NV], grad[D::NV], search[D::NV], Mv[D::NV];
+    T jar_f[D::NFRIC], jv_f[D::NFRIC], jar_l[D::NVA], jv_l[D::NVA], jarb[D::MAXCON][4], jvb[D::MAXCON][4];
+    T Z[D::NVA][6], Bm[6][D::NVA];   // coupled case: A^{-1} B and B^T of the pad-touched chain block (Schur complement)
+  };
   union {
     StageA a;
-    StageB b;
-    StageC c;
+    StageT t;
+    typename std::conditional<TPE_ && sizeof(T) == 4, EmptyStage, StageB>::type b;
+    typename std::conditional<TPE_, EmptyStage, StageC>::type c;   // the thread-per-env mapping has its own solver scratch (t)
   };
 };
+template <class E> KM_HD typename E::StageB& stage_b(E& e, typename E::StageB& local) {
+  if constexpr (E::TPE && sizeof(e.qpos[0]) == 4) return local;
+  else return e.b;
+}
 
 // efc row descriptor: type | id << 2 | k << 10 | neg << 12   (id = dof for friction/limit rows, contact for contact rows;
 // k = 1..3 pyramid edge; neg = row uses the negative edge / limit row has J = -e)

@@ -11,8 +11,9 @@
 
 namespace km {
 
-#define KM_TPL template <class S, typename T, int G>
-#define KM_ARGS Env<S, T>& e, const Model<S, T>& m, const Grp<G>& g
+// E is the env working-set type (Env<S, T, TPE>); it is always deduced from the argument
+#define KM_TPL template <class S, typename T, int G, class E>
+#define KM_ARGS E& e, const Model<S, T>& m, const Grp<G>& g
 
 // =========================================================================================== position stage
 // mj_kinematics for the articulated links (level by level) and the cube.
@@ -100,7 +101,7 @@ KM_TPL KM_FN void com_crb(KM_ARGS) {
 
 // Dense Cholesky A = L L^T of the leading n x n block, one lane per row, in place (strict lower triangle
 // holds L, diag[] holds the pivots).  A has row stride `ld`.
-KM_TPL KM_FN void chol_factor(T* A, T* diag, int n, int ld, const Grp<G>& g) {
+template <class S, typename T, int G> KM_FN void chol_factor(T* A, T* diag, int n, int ld, const Grp<G>& g) {
   for (int j = 0; j < n; j++) {
     for (int i = j + g.lane; i < n; i += G) {
       T s = A[i * ld + j];
@@ -117,7 +118,7 @@ KM_TPL KM_FN void chol_factor(T* A, T* diag, int n, int ld, const Grp<G>& g) {
   }
 }
 // x <- A^{-1} x for a factor produced by chol_factor
-KM_TPL KM_FN void chol_solve(const T* A, const T* diag, T* x, int n, int ld, const Grp<G>& g) {
+template <class S, typename T, int G> KM_FN void chol_solve(const T* A, const T* diag, T* x, int n, int ld, const Grp<G>& g) {
   for (int j = 0; j < n; j++) {
     const T y = x[j] / diag[j];
     g.sync();
@@ -139,7 +140,7 @@ KM_TPL KM_FN void chol_solve(const T* A, const T* diag, T* x, int n, int ld, con
 }
 
 // contact Jacobian base row b of contact c at dof col (col must lie in the contact's support)
-template <class S, typename T> KM_HD T jc(const Env<S, T>& e, int c, int b, int col) {
+template <class S, typename T, class E> KM_HD T jc(const E& e, int c, int b, int col) {
   typedef Dim<S> D;
   return col >= D::NVA ? e.Jq[c][b][col - D::NVA] : e.Ja[e.con_slot[c] < D::NPAD ? e.con_slot[c] : 0][b][col];
 }
@@ -151,11 +152,12 @@ template <class S, typename T> KM_HD T jc(const Env<S, T>& e, int c, int b, int 
 // (other kinematic chains; the cube while no finger pad touches it).  The body is branch-free on purpose: ptxas
 // wraps every shuffle that follows a potentially divergent branch in a WARPSYNC.COLLECTIVE sequence.
 // Host build (tests only): plain dense Cholesky.
-template <class S, typename T, int G, bool DENSE> KM_FN void solve_spd(KM_ARGS, const T* rhs, T* dst) {
+template <class S, typename T, int G, bool DENSE, class E> KM_FN void solve_spd(KM_ARGS, const T* rhs, T* dst) {
   typedef Dim<S> D;
   typedef Num<T> N;
   constexpr int NV = D::NV;
 #if defined(__CUDA_ARCH__)
+  if constexpr (G > 1) {
   static_assert(G >= NV, "one lane per dof row");
   g.sync();
   const int i = g.lane, ic = i < NV ? i : NV - 1;   // surplus lanes shadow the last row
@@ -201,16 +203,19 @@ template <class S, typename T, int G, bool DENSE> KM_FN void solve_spd(KM_ARGS, 
   });
   dst[ic] = x;
   g.sync();
-#else
-  if (dst != rhs)
-    for (int i = 0; i < NV; i++) dst[i] = rhs[i];
-  chol_factor<S, T, G>(&e.c.H[0][0], e.c.Hd, NV, D::HS, g);
-  chol_solve<S, T, G>(&e.c.H[0][0], e.c.Hd, dst, NV, D::HS, g);
+  return;
+  }
 #endif
+  if constexpr (G == 1) {
+    if (dst != rhs)
+      for (int i = 0; i < NV; i++) dst[i] = rhs[i];
+    chol_factor<S, T, G>(&e.c.H[0][0], e.c.Hd, NV, D::HS, g);
+    chol_solve<S, T, G>(&e.c.H[0][0], e.c.Hd, dst, NV, D::HS, g);
+  }
 }
 
 // one lower-triangle entry (i >= j) of J^T diag(D_active) J restricted to the contacts
-KM_TPL KM_HD T hess_contacts(const Env<S, T>& e, int i, int j) {
+KM_TPL KM_HD T hess_contacts(const E& e, int i, int j) {
   T h = 0;
   for (int c = 0; c < e.ncon; c++) {
     const unsigned sup = e.con_sup[c];
@@ -582,6 +587,10 @@ KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
   g.sync();
 }
 
+}  // namespace km
+#include "km_solver_tpe.cuh"
+namespace km {
+
 // =========================================================================================== acceleration stage
 // mj_fwdActuation (<position kp> servos) + mj_fwdAcceleration.
 KM_TPL KM_FN void fwd_actuation_acceleration(KM_ARGS) {
@@ -594,11 +603,14 @@ KM_TPL KM_FN void fwd_actuation_acceleration(KM_ARGS) {
     }
     const T s = f - e.bias[i];
     e.qfrc_smooth[i] = s;
-    e.c.hdiag[i] = 0;
+    if constexpr (G > 1) e.c.hdiag[i] = 0;
   }
   g.sync();
-  assemble_h<S, T, G>(e, m, g, false);
-  solve_spd<S, T, G, false>(e, m, g, e.qfrc_smooth, e.qacc_smooth);
+  if constexpr (G == 1) tpe_solveM<S, T>(e, m, e.qfrc_smooth, e.qacc_smooth);
+  else {
+    assemble_h<S, T, G>(e, m, g, false);
+    solve_spd<S, T, G, false>(e, m, g, e.qfrc_smooth, e.qacc_smooth);
+  }
 }
 
 // ---- Newton solver (mj_solNewton on the primal problem)
@@ -836,13 +848,14 @@ KM_TPL KM_HD void step2(KM_ARGS) {
   g.cta_sync();
   fwd_actuation_acceleration<S, T, G>(e, m, g);
   g.cta_sync();
-  fwd_constraint<S, T, G>(e, m, g);
+  if constexpr (G == 1) fwd_constraint_tpe<S, T>(e, m);
+  else fwd_constraint<S, T, G>(e, m, g);
   euler<S, T, G>(e, m, g);
 }
 
 // =========================================================================================== task: action decode + IK
 // site pose of arm a from the current link frames
-KM_TPL KM_HD void site_pose(const Env<S, T>& e, const Model<S, T>& m, int a, T* pos, T* mat) {
+KM_TPL KM_HD void site_pose(const E& e, const Model<S, T>& m, int a, T* pos, T* mat) {
   const int l = m.arm_site_link[a];
   T t[3], q[4];
   mulv3(t, e.xmat[l], m.site_pos[a]);
@@ -877,7 +890,7 @@ template <typename T> KM_HD void euler_xyz_ext_to_quat(T* q, const T* eul) {
 
 // forward kinematics of arm a's chain at joint values b.x (masked joints) / qpos (the others): per-link axis and
 // anchor, site pose.  One lane.
-KM_TPL KM_HD void ik_chain_fk(Env<S, T>& e, const Model<S, T>& m, int a, const double* x) {
+template <class S, typename T, int G, class E, class B> KM_HD void ik_chain_fk(E& e, B& b, const Model<S, T>& m, int a, const double* x) {
   typedef Num<double> N;
   double q[4] = {1, 0, 0, 0}, pos[3] = {0, 0, 0}, mat[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   for (int k = 0; k < m.arm_nchain[a]; k++) {
@@ -894,28 +907,28 @@ KM_TPL KM_HD void ik_chain_fk(Env<S, T>& e, const Model<S, T>& m, int a, const d
     } else { q[0] = ql[0]; q[1] = ql[1]; q[2] = ql[2]; q[3] = ql[3]; }
     qnormalize(q);
     q2mat(mat, q);
-    for (int i = 0; i < 3; i++) { e.b.an[k][i] = pos[i]; e.b.ax[k][i] = mat[3 * i + 2]; }
+    for (int i = 0; i < 3; i++) { b.an[k][i] = pos[i]; b.ax[k][i] = mat[3 * i + 2]; }
     if (m.jtype[l] == JT_SLIDE) { pos[0] += mat[2] * th; pos[1] += mat[5] * th; pos[2] += mat[8] * th; }
   }
   double t[3], sq[4];
   mulv3(t, mat, m.dk_site_pos[a]);
-  for (int i = 0; i < 3; i++) e.b.spos[i] = pos[i] + t[i];
+  for (int i = 0; i < 3; i++) b.spos[i] = pos[i] + t[i];
   qmul(sq, q, m.dk_site_quat[a]);
-  q2mat(e.b.smat, sq);
+  q2mat(b.smat, sq);
 }
 
 // ik_res (reference ik_mujoco.py:20-53) from the chain pose currently in e.b; pose rows by lane 0, regularisers by all
-KM_TPL KM_HD void ik_residual(KM_ARGS, int a, const double* x, double* res) {
+template <class S, typename T, int G, class E, class B> KM_HD void ik_residual(E& e, B& b, const Model<S, T>& m, const Grp<G>& g, int a, const double* x, double* res) {
   const int n = m.arm_nmask[a];
   if (g.lane == 0) {
     double cur[4], rq[3];
-    for (int i = 0; i < 3; i++) res[i] = e.b.spos[i] - e.b.goal[i];
-    mat2quat(cur, e.b.smat);
-    subquat(rq, e.b.goal + 3, cur);
+    for (int i = 0; i < 3; i++) res[i] = b.spos[i] - b.goal[i];
+    mat2quat(cur, b.smat);
+    subquat(rq, b.goal + 3, cur);
     for (int i = 0; i < 3; i++) res[3 + i] = rq[i] * 0.02;                        // IK_RES_RAD
   }
   KM_FOR(i, n) {
-    res[6 + i] = 6e-3 * (x[i] - e.b.qprev[i]);                                     // IK_RES_REG_PREV
+    res[6 + i] = 6e-3 * (x[i] - b.qprev[i]);                                     // IK_RES_REG_PREV
     res[6 + n + i] = 2e-6 * (x[i] - m.dk_qhome[m.arm_mask[a][i]]);                 // IK_RES_REG_HOME
   }
   g.sync();
@@ -923,14 +936,14 @@ KM_TPL KM_HD void ik_residual(KM_ARGS, int a, const double* x, double* res) {
 
 // pose rows of ik_jac (reference ik_mujoco.py:56-97): [Jp ; rad * d subQuat(goal, cur) / dq], columns = mask.
 // The orientation block is -rad * Jl^{-1}(phi) R_site^T Jr with phi = subQuat(goal, cur)  (DESIGN.md).
-KM_TPL KM_HD void ik_jacobian(KM_ARGS, int a) {
+template <class S, typename T, int G, class E, class B> KM_HD void ik_jacobian(E& e, B& b, const Model<S, T>& m, const Grp<G>& g, int a) {
   typedef Num<double> N;
   const int n = m.arm_nmask[a];
   KM_FOR(c, n) {
-    const double* R = e.b.smat;
+    const double* R = b.smat;
     double cur[4], phi[3];
     mat2quat(cur, R);
-    subquat(phi, e.b.goal + 3, cur);
+    subquat(phi, b.goal + 3, cur);
     double u[3] = {phi[0], phi[1], phi[2]};
     const double half = 0.5 * normalize3(u);
     const double coef = 1.0 - (half < 6e-8 ? 1.0 : half / N::tan(half));
@@ -943,18 +956,18 @@ KM_TPL KM_HD void ik_jacobian(KM_ARGS, int a) {
         Dm[3 * i + j] = (i == j ? 1.0 : 0.0) - half * K[3 * i + j] + coef * kk;
       }
     const int k = m.arm_mask_chain[a][c];   // position of masked joint c in the chain
-    const double* ax = e.b.ax[k];
+    const double* ax = b.ax[k];
     double jp[3], jr[3] = {0, 0, 0};
     if (m.jtype[m.arm_mask[a][c]] == JT_SLIDE) { jp[0] = ax[0]; jp[1] = ax[1]; jp[2] = ax[2]; }
     else {
-      const double o[3] = {e.b.spos[0] - e.b.an[k][0], e.b.spos[1] - e.b.an[k][1], e.b.spos[2] - e.b.an[k][2]};
+      const double o[3] = {b.spos[0] - b.an[k][0], b.spos[1] - b.an[k][1], b.spos[2] - b.an[k][2]};
       cross3(jp, ax, o);
       jr[0] = ax[0]; jr[1] = ax[1]; jr[2] = ax[2];
     }
     double jl[3], o3[3];
     mulTv3(jl, R, jr);
     mulv3(o3, Dm, jl);
-    for (int i = 0; i < 3; i++) { e.b.J[i][c] = jp[i]; e.b.J[3 + i][c] = -0.02 * o3[i]; }   // IK_JAC_RAD
+    for (int i = 0; i < 3; i++) { b.J[i][c] = jp[i]; b.J[3 + i][c] = -0.02 * o3[i]; }   // IK_JAC_RAD
   }
   g.sync();
 }
@@ -966,12 +979,15 @@ KM_TPL KM_HD void ik_jacobian(KM_ARGS, int a) {
 // leaving qpos[mask] at the solution (B-1).  Skipped when x0 is out of bounds (B-4).
 KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
   typedef Dim<S> D;
+  // the IK scratch is fp64; the thread-per-env working set holds no 8-byte members, so there it is a local
+  typename E::StageB blocal;
+  typename E::StageB& b = stage_b(e, blocal);
   const int n = m.arm_nmask[a], nr = 6 + 2 * n;
   bool bad = false;
   KM_FOR(i, n) {
     const int j = m.arm_mask[a][i];
     const double x = (double)e.qpos[j];
-    e.b.x[i] = x; e.b.qprev[i] = x; e.b.lo[i] = m.dk_range[j][0]; e.b.hi[i] = m.dk_range[j][1];
+    b.x[i] = x; b.qprev[i] = x; b.lo[i] = m.dk_range[j][0]; b.hi[i] = m.dk_range[j][1];
     bad = bad || x < m.dk_range[j][0] || x > m.dk_range[j][1];
   }
   const bool feasible = !g.any(bad);
@@ -979,72 +995,72 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
   if (g.lane == 0) {
     // goal = current site pose displaced by the action (EE_POS_DELTA 0.01, EE_ORN_DELTA 0.1, extrinsic xyz Euler)
     double eul[3];
-    ik_chain_fk<S, T, G>(e, m, a, e.b.x);
-    for (int i = 0; i < 3; i++) e.b.goal[i] = (double)act[m.off_pos[a] + i] * 0.01 + e.b.spos[i];
-    mat_to_euler_xyz_ext(eul, e.b.smat);
+    ik_chain_fk<S, T, G>(e, b, m, a, b.x);
+    for (int i = 0; i < 3; i++) b.goal[i] = (double)act[m.off_pos[a] + i] * 0.01 + b.spos[i];
+    mat_to_euler_xyz_ext(eul, b.smat);
     for (int i = 0; i < 3; i++) eul[i] = (double)act[m.off_orn[a] + i] * 0.1 + eul[i];
-    euler_xyz_ext_to_quat(e.b.goal + 3, eul);
-    for (int i = 0; i < 7; i++) e.mocap[7 * m.arm_mocap[a] + i] = (T)e.b.goal[i];
+    euler_xyz_ext_to_quat(b.goal + 3, eul);
+    for (int i = 0; i < 7; i++) e.mocap[7 * m.arm_mocap[a] + i] = (T)b.goal[i];
   }
   g.sync();
   if (feasible) {
     const double lam = 9e-3 * (6e-3 + 2e-6), reg = 9e-3;   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)
     double mu = 0;
-    ik_residual<S, T, G>(e, m, g, a, e.b.x, e.b.r);
-    ik_jacobian<S, T, G>(e, m, g, a);
+    ik_residual<S, T, G>(e, b, m, g, a, b.x, b.r);
+    ik_jacobian<S, T, G>(e, b, m, g, a);
     double cs = 0;
-    KM_FOR(k, nr) cs += 0.5 * e.b.r[k] * e.b.r[k];
+    KM_FOR(k, nr) cs += 0.5 * b.r[k] * b.r[k];
     double cost = g.sum(cs);
     for (int it = 0; it < m.ik_iters; it++) {
       KM_FOR(i, n) {
         double gi = 0;
-        for (int k = 0; k < 6; k++) gi += e.b.J[k][i] * e.b.r[k];
-        gi += reg * e.b.r[6 + i] + reg * e.b.r[6 + n + i];
-        e.b.gv[i] = -gi;
-        e.b.active[i] = (e.b.x[i] <= e.b.lo[i] && gi > 0.0) || (e.b.x[i] >= e.b.hi[i] && gi < 0.0);
+        for (int k = 0; k < 6; k++) gi += b.J[k][i] * b.r[k];
+        gi += reg * b.r[6 + i] + reg * b.r[6 + n + i];
+        b.gv[i] = -gi;
+        b.active[i] = (b.x[i] <= b.lo[i] && gi > 0.0) || (b.x[i] >= b.hi[i] && gi < 0.0);
       }
       g.sync();
       KM_FOR(w, n * n) {
         const int i = w / n, j = w - i * n;
         if (j > i) continue;
         double sacc = 0;
-        if (e.b.active[i] || e.b.active[j]) sacc = i == j ? 1.0 : 0.0;
+        if (b.active[i] || b.active[j]) sacc = i == j ? 1.0 : 0.0;
         else {
-          for (int k = 0; k < 6; k++) sacc += e.b.J[k][i] * e.b.J[k][j];
+          for (int k = 0; k < 6; k++) sacc += b.J[k][i] * b.J[k][j];
           if (i == j) sacc += lam + mu;
         }
-        e.b.A[i][j] = sacc;
+        b.A[i][j] = sacc;
       }
       g.sync();
       if (g.lane == 0) {   // 7 x 7 Cholesky and the two triangular solves
-        for (int i = 0; i < n; i++) if (e.b.active[i]) e.b.gv[i] = 0;
+        for (int i = 0; i < n; i++) if (b.active[i]) b.gv[i] = 0;
         for (int j = 0; j < n; j++) {
-          double d = e.b.A[j][j];
-          for (int k = 0; k < j; k++) d -= e.b.A[j][k] * e.b.A[j][k];
+          double d = b.A[j][j];
+          for (int k = 0; k < j; k++) d -= b.A[j][k] * b.A[j][k];
           d = Num<double>::sqrt(d);
-          e.b.A[j][j] = d;
+          b.A[j][j] = d;
           for (int i = j + 1; i < n; i++) {
-            double u = e.b.A[i][j];
-            for (int k = 0; k < j; k++) u -= e.b.A[i][k] * e.b.A[j][k];
-            e.b.A[i][j] = u / d;
+            double u = b.A[i][j];
+            for (int k = 0; k < j; k++) u -= b.A[i][k] * b.A[j][k];
+            b.A[i][j] = u / d;
           }
         }
-        for (int i = 0; i < n; i++) { double t = e.b.gv[i]; for (int k = 0; k < i; k++) t -= e.b.A[i][k] * e.b.gv[k]; e.b.gv[i] = t / e.b.A[i][i]; }
-        for (int i = n - 1; i >= 0; i--) { double t = e.b.gv[i]; for (int k = i + 1; k < n; k++) t -= e.b.A[k][i] * e.b.gv[k]; e.b.gv[i] = t / e.b.A[i][i]; }
-        for (int i = 0; i < n; i++) e.b.xn[i] = tclip(e.b.x[i] + e.b.gv[i], e.b.lo[i], e.b.hi[i]);
-        ik_chain_fk<S, T, G>(e, m, a, e.b.xn);
+        for (int i = 0; i < n; i++) { double t = b.gv[i]; for (int k = 0; k < i; k++) t -= b.A[i][k] * b.gv[k]; b.gv[i] = t / b.A[i][i]; }
+        for (int i = n - 1; i >= 0; i--) { double t = b.gv[i]; for (int k = i + 1; k < n; k++) t -= b.A[k][i] * b.gv[k]; b.gv[i] = t / b.A[i][i]; }
+        for (int i = 0; i < n; i++) b.xn[i] = tclip(b.x[i] + b.gv[i], b.lo[i], b.hi[i]);
+        ik_chain_fk<S, T, G>(e, b, m, a, b.xn);
       }
       g.sync();
-      ik_residual<S, T, G>(e, m, g, a, e.b.xn, e.b.rn);
+      ik_residual<S, T, G>(e, b, m, g, a, b.xn, b.rn);
       double cn = 0;
-      KM_FOR(k, nr) cn += 0.5 * e.b.rn[k] * e.b.rn[k];
+      KM_FOR(k, nr) cn += 0.5 * b.rn[k] * b.rn[k];
       const double costn = g.sum(cn);
       if (costn <= cost) {
-        KM_FOR(i, n) e.b.x[i] = e.b.xn[i];
-        KM_FOR(k, nr) e.b.r[k] = e.b.rn[k];
+        KM_FOR(i, n) b.x[i] = b.xn[i];
+        KM_FOR(k, nr) b.r[k] = b.rn[k];
         g.sync();
         cost = costn;
-        ik_jacobian<S, T, G>(e, m, g, a);
+        ik_jacobian<S, T, G>(e, b, m, g, a);
         mu = mu * 0.25;
         if (mu < 1e-6) mu = 0;
       } else {
@@ -1054,9 +1070,9 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
   }
   KM_FOR(i, n) {
     const int j = m.arm_mask[a][i];
-    const float q = (float)tclip(e.b.x[i], e.b.lo[i], e.b.hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
+    const float q = (float)tclip(b.x[i], b.lo[i], b.hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
     e.ctrl[j] = (T)q;
-    if (feasible && m.ik_teleport) e.qpos[j] = (T)e.b.x[i];
+    if (feasible && m.ik_teleport) e.qpos[j] = (T)b.x[i];
   }
   g.sync();
 }

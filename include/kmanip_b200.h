@@ -100,6 +100,9 @@ typedef struct km_step_out {
 
 const char* km_last_error(void);
 const char* km_version(void);
+/* Measured FMA throughput of the CUDA-core pipe this path is bound by (dtype KM_F32 / KM_F64), in TFLOP/s: the
+   denominator of the FP roofline that bench.py reports (MEASURED_PEAKS.json carries no CUDA-core figure). */
+int km_measure_fma_peak(int device, int dtype, double* tflops);
 
 /* scene: KM_SCENE_*; dtype: KM_F32 / KM_F64; seed/env0: cube-spawn RNG key and the global id of env 0 of this shard. */
 int km_create(const km_model* model, const km_task* task, int scene, int n_envs, int device, int dtype,

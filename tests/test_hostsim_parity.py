@@ -42,7 +42,9 @@ def test_sub_step_stages_match_oracle_fp64(env_id):
             hs.step2()
             assert rel_err(hs.field("qacc_smooth"), o.field("qacc_smooth")) < 1e-10
             assert rel_err(hs.field("qacc"), o.field("qacc")) < 1e-9
-            assert rel_err(hs.field("efc_force"), o.field("efc_force")) < 1e-8
+            # constraint force in joint space, from the equation of motion (the thread-per-env solver keeps no row forces)
+            qfc = hs.field("qM").reshape(hs.nv, hs.nv) @ hs.field("qacc") - hs.field("qfrc_smooth")
+            assert rel_err(qfc, o.field("qfrc_constraint"), floor=1.0) < 1e-8
             a, b = hs.get_state(), o.get_state()
             assert rel_err(a["qpos"], b["qpos"]) < 1e-12 and rel_err(a["qvel"], b["qvel"]) < 1e-11
 
@@ -95,3 +97,45 @@ def test_reset_matches_oracle_spawn():
             assert np.allclose(hs.get_state()["qpos"][-7:-4], xyz, atol=1e-15)
             assert np.allclose(obs, o.reset(xyz), atol=1e-14)
             assert 0.1 <= xyz[0] <= 0.3 and 0.5 <= xyz[1] <= 0.7 and 0.6 <= xyz[2] <= 0.7
+
+
+@pytest.mark.parametrize("env_id", ["KManipSoloArm", "KManipDualArm", "KManipTorso"])
+def test_finger_pad_contacts_match_oracle(env_id):
+    """Coupled case: the cube is placed against the finger pads (and, in half of the cases, on the table too) so that
+    pad contacts couple the arm and cube blocks of the solver's Hessian."""
+    o = om.Oracle(env_id)
+    hs = hostsim.HostSim(env_id, 64)
+    st0 = om.batch_reset_state(o, 1, seed=1)
+    rng = np.random.default_rng(3)
+    pads = [i for i, nm in enumerate(o.flat["geom_name"]) if nm.startswith("finger_pad")]
+    seen = 0
+    for trial in range(8):
+        qpos = st0["qpos"][0].copy()
+        qpos[: o.nu] += rng.uniform(-0.05, 0.05, o.nu) * (np.arange(o.nu) < o.nu)
+        rngs = np.array(o.flat["jnt_range"])[: o.nu]
+        qpos[: o.nu] = np.clip(qpos[: o.nu], rngs[:, 0] + 1e-3, rngs[:, 1] - 1e-3)
+        o.set_state(qpos, np.zeros(o.nv), qpos[: o.nu])
+        gx = o.field("geom_xpos").reshape(-1, 3)
+        p = gx[pads[trial % len(pads)]]
+        # cube face 2 mm inside the pad sphere (radius 0.01), approached along a random axis
+        ax = trial % 3
+        off = np.zeros(3)
+        off[ax] = (0.02 + 0.01 - 0.002) * (1 if trial % 2 else -1)
+        qpos[-7:-4] = p + off
+        qpos[-4:] = [1, 0, 0, 0]
+        qvel = rng.normal(size=o.nv) * 0.1
+        state = dict(qpos=qpos, qvel=qvel, ctrl=qpos[: o.nu].copy(), warm=np.zeros(o.nv), mocap=st0["mocap"][0][: 7 * o.nmocap].copy(), time=0.0)
+        o.set_state(state["qpos"], state["qvel"], state["ctrl"], state["warm"], 0.0, state["mocap"] if o.nmocap else None)
+        r, fl = o.reward(with_flags=True)
+        if not fl & 6:
+            continue
+        seen += 1
+        act = rng.uniform(-1, 1, o.task.act_dim).astype(np.float32)
+        hs.set_state(state)
+        out = hs.env_step(act)
+        o.set_state(state["qpos"], state["qvel"], state["ctrl"], state["warm"], 0.0, state["mocap"] if o.nmocap else None)
+        obs, rew = o.step(act)
+        a, b = hs.get_state(), o.get_state()
+        assert rel_err(a["qpos"], b["qpos"]) < 1e-10 and rel_err(a["qvel"], b["qvel"], floor=1.0) < 1e-9, (trial, rel_err(a["qvel"], b["qvel"]))
+        assert rel_err(out["obs"], obs, floor=1.0) < 1e-9
+    assert seen >= 4
