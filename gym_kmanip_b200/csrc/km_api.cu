@@ -78,13 +78,15 @@ static int configure(km_sim* h, int G, int epb) {
   const int fit = (int)(((size_t)dev_smem - model_b) / h->vt.env_bytes);
   const int cap = fit * G > h->vt.max_threads ? h->vt.max_threads / G : fit;
   if (epb == 0) {
-    // default: one CTA per SM holding as many envs as shared memory allows, shrunk so that the waves are balanced
-    // (4096 envs on 148 SMs -> 28 envs per CTA, a single wave)
+    // default: fill the shared memory of every SM with envs, shrunk so that the waves are balanced (4096 envs on 148 SMs
+    // -> 28 per SM, a single wave); when an SM holds 16 or more, split them over two CTAs -- the CTA-wide lockstep then
+    // couples fewer envs (measured +6..8 % for the solo-arm scene, profiles/r01_notes.md)
     if (cap < 1) return fail(KM_ERR_ARG, "an env does not fit in shared memory");
     const long per_wave = (long)h->num_sms * cap;
     const long waves = ((long)h->n + per_wave - 1) / per_wave;
-    epb = (int)(((long)h->n + h->num_sms * waves - 1) / (h->num_sms * waves));
-    if (epb > cap) epb = cap;
+    int per_sm = (int)(((long)h->n + h->num_sms * waves - 1) / (h->num_sms * waves));
+    if (per_sm > cap) per_sm = cap;
+    epb = per_sm >= 16 ? (per_sm + 1) / 2 : per_sm;
   }
   if (epb < 1 || epb > cap) return fail(KM_ERR_ARG, "envs_per_block out of range for this scene / precision");
   if (model_b + (size_t)epb * h->vt.env_bytes > (size_t)dev_smem)

@@ -33,12 +33,14 @@ def _sim_state(sim):
     return out
 
 
-def _run(env_id, dtype, n, steps, tol_pos, tol_vel, tol_obs):
+def _run(env_id, dtype, n, steps, tol_pos, tol_vel, tol_obs, lanes=0):
     import torch
     from gym_kmanip_b200.batch_sim import BatchSim
     f32 = dtype == "float32"
     o, traj = oracle_rollout(env_id, n, steps, seed=3, action_seed=5, round32=f32)
     sim = BatchSim(env_id, n, dtype=dtype, seed=3)
+    if lanes:
+        assert sim.configure(lanes, 0)["lanes_per_env"] == lanes
     worst = dict(qpos=0.0, qvel=0.0, ctrl=0.0, obs=0.0, reward=0.0, c_pos=0.0, c_vel=0.0)
     n_touch = n_flip = 0
     for t, rec in enumerate(traj):
@@ -94,6 +96,18 @@ def test_env_step_parity_fp64(env_id):
 @pytest.mark.parametrize("env_id", ENVS)
 def test_env_step_parity_fp32(env_id):
     _run(env_id, "float32", n=64, steps=70, tol_pos=2e-5, tol_vel=1e-4, tol_obs=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", ["KManipSoloArm", "KManipDualArm", "KManipTorso", "KManipSoloArmQPos"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_thread_per_env_mapping_parity(env_id, dtype):
+    """The thread-per-env mapping (km_configure(h, 1, 0): k_env_step_tpe with its own Newton solver) against the oracle,
+    same tolerances as the lane-group mapping."""
+    if dtype == "float64":
+        _run(env_id, dtype, n=64, steps=70, tol_pos=1e-10, tol_vel=1e-10, tol_obs=1e-9, lanes=1)
+    else:
+        _run(env_id, dtype, n=64, steps=70, tol_pos=2e-5, tol_vel=1e-4, tol_obs=1e-3, lanes=1)
 
 
 @pytest.mark.gpu
