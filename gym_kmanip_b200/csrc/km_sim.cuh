@@ -241,8 +241,20 @@ KM_TPL KM_HD void assemble_h(KM_ARGS, bool with_contacts) {
     if (i < D::NVA) h = e.M[i][j];
     else h = i == j ? (i - D::NVA < 3 ? m.cube_mass : m.cube_inertia[i - D::NVA - 3]) : T(0);
     if (i == j) h += e.c.hdiag[i];
-    // contact terms: the cube block always; arm rows only while a finger pad touches the cube
-    if (with_contacts && (e.coupled || j >= D::NVA)) h += hess_contacts<S, T, G>(e, i, j);
+    // contact terms: the cube block always (every contact has cube columns: direct loads, no support test);
+    // arm rows only while a finger pad touches the cube
+    if (with_contacts && j >= D::NVA) {
+      const int ki = i - D::NVA, kj = j - D::NVA;
+      for (int c = 0; c < e.ncon; c++) {
+        const T ni = e.Jq[c][0][ki], nj = e.Jq[c][0][kj];
+        T acc = e.cb[c][0] * ni * nj;
+        for (int k = 1; k < 4; k++) {
+          const T ti = e.Jq[c][k][ki], tj = e.Jq[c][k][kj];
+          acc += e.cb[c][k] * (ni * tj + ti * nj) + e.con_W[c][k - 1] * ti * tj;
+        }
+        h += acc;
+      }
+    } else if (with_contacts && e.coupled) h += hess_contacts<S, T, G>(e, i, j);
     e.c.H[i][j] = h;
   }
   g.sync();
@@ -480,10 +492,16 @@ KM_TPL KM_FN void mul_JT_force(KM_ARGS) {
     const int fr = m.dof_fric[i], lr = i < D::NVA ? e.dof_lim[i] : -1;
     if (fr >= 0) s += e.c.efc_force[fr];
     if (lr >= 0) s += efc_neg(e.efc_desc[lr]) ? -e.c.efc_force[lr] : e.c.efc_force[lr];
-    for (int c = 0; c < e.ncon; c++)
-      if ((e.con_sup[c] >> i) & 1u)
-        s += jc<S, T>(e, c, 0, i) * e.cb[c][0] + jc<S, T>(e, c, 1, i) * e.cb[c][1] + jc<S, T>(e, c, 2, i) * e.cb[c][2] +
-             jc<S, T>(e, c, 3, i) * e.cb[c][3];
+    if (i >= D::NVA) {   // cube columns: every contact, direct loads
+      const int k = i - D::NVA;
+      for (int c = 0; c < e.ncon; c++)
+        s += e.Jq[c][0][k] * e.cb[c][0] + e.Jq[c][1][k] * e.cb[c][1] + e.Jq[c][2][k] * e.cb[c][2] + e.Jq[c][3][k] * e.cb[c][3];
+    } else if (e.coupled) {
+      for (int c = 0; c < e.ncon; c++)
+        if ((e.con_sup[c] >> i) & 1u)
+          s += jc<S, T>(e, c, 0, i) * e.cb[c][0] + jc<S, T>(e, c, 1, i) * e.cb[c][1] + jc<S, T>(e, c, 2, i) * e.cb[c][2] +
+               jc<S, T>(e, c, 3, i) * e.cb[c][3];
+    }
     e.c.qfc[i] = s;
   }
   g.sync();
@@ -498,9 +516,11 @@ KM_TPL KM_FN void mul_M(KM_ARGS, const T* x, T* out) {
       const int k = i - D::NVA;
       s = (k < 3 ? m.cube_mass : m.cube_inertia[k - 3]) * x[i];
     } else {
+      // dense row: entries between unrelated links are structural zeros (init_env), and independent loads beat
+      // walking the parent chain (a dependent load per ancestor)
       s = 0;
-      for (int j = m.parent[i]; j >= 0; j = m.parent[j]) s += e.M[i][j] * x[j];
-      for (int j = i; j < m.sub_end[i]; j++) s += e.M[i][j] * x[j];
+#pragma unroll
+      for (int j = 0; j < D::NVA; j++) s += e.M[i][j] * x[j];
     }
     out[i] = s;
   }
