@@ -17,7 +17,7 @@ SCENE_ID = {"solo_arm": 0, "dual_arm": 1, "torso": 2}
 class BatchSim:
     def __init__(self, env_id: str, num_envs: int, device: int = 0, dtype: str = "float32", seed: int = 0, env0: int = 0,
                  ik_iters: int = K.DEVICE_IK_ITERS, ik_teleport: bool = True, max_episode_steps: int = K.MAX_EPISODE_STEPS,
-                 env_kwargs: Optional[dict] = None):
+                 env_kwargs: Optional[dict] = None, ik_mode: int = 0):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("gym_kmanip_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -29,7 +29,7 @@ class BatchSim:
         self.flat = mjcf.load_flat(self.scene)
         self.pm = flatmodel.PackedModel(self.flat)
         self.task = flatmodel.make_task(self.flat, self.kw, ik_iters=ik_iters, ik_teleport=ik_teleport,
-                                        max_episode_steps=max_episode_steps)
+                                        max_episode_steps=max_episode_steps, ik_mode=ik_mode)
         self.n = int(num_envs)
         self.device_index = int(device)
         self.device = torch.device("cuda", self.device_index)

@@ -240,7 +240,7 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
     m.arm_mocap[a] = tk->arm_mocap[a];
     m.off_pos[a] = tk->off_pos[a]; m.off_orn[a] = tk->off_orn[a]; m.off_grip[a] = tk->off_grip[a]; m.off_q[a] = tk->off_q[a];
   }
-  m.ik_iters = tk->ik_iters; m.ik_teleport = tk->ik_teleport; m.max_episode_steps = tk->max_episode_steps;
+  m.ik_iters = tk->ik_iters; m.ik_teleport = tk->ik_teleport; m.ik_mode = tk->ik_mode; m.max_episode_steps = tk->max_episode_steps;
   for (int i = 0; i < D::QLEN; i++) { m.q_home[i] = (T)tk->q_home[i]; m.dk_qhome[i] = tk->q_home[i]; }
   for (int i = 0; i < 3; i++) {
     m.spawn_lo[i] = (T)tk->cube_spawn_lo[i]; m.spawn_hi[i] = (T)tk->cube_spawn_hi[i];

@@ -89,7 +89,7 @@ template <class S, typename T> struct Model {
   // fp64 copies for the IK (kinematic chain of each arm from its base to the site link)
   int arm_nchain[2], arm_chain[2][D::MAXLEVEL], arm_chain_mask[2][D::MAXLEVEL], arm_mask_chain[2][D::MAXMASK];
   double dk_lpos[D::NVA][3], dk_lquat[D::NVA][4], dk_site_pos[2][3], dk_site_quat[2][4], dk_range[D::NVA][2], dk_qhome[D::QLEN];
-  int ik_iters, ik_teleport, max_episode_steps;
+  int ik_iters, ik_teleport, max_episode_steps, ik_mode;
   T q_home[D::QLEN], spawn_lo[3], spawn_hi[3], cube_quat0[4], mocap0[D::NMOCAP * 7];
   double spawn_lo_d[3], spawn_hi_d[3];
 };

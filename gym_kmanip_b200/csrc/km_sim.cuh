@@ -992,6 +992,10 @@ template <class S, typename T, int G, class E, class B> KM_HD void ik_jacobian(E
   g.sync();
 }
 
+}  // namespace km
+#include "km_ik_trf.cuh"
+namespace km {
+
 // Device IK of one arm, fused in front of the sub-steps: end-effector target from the action (reference
 // env_sim.py:60-70, 80-90), then projected Levenberg-Marquardt on the reference's stationarity condition J^T r = 0
 // with J, r exactly as ik_jac / ik_res build them (including their mismatched regulariser weights),
@@ -1023,7 +1027,11 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
     for (int i = 0; i < 7; i++) e.mocap[7 * m.arm_mocap[a] + i] = (T)b.goal[i];
   }
   g.sync();
-  if (feasible) {
+  if (feasible && m.ik_mode == 1) {
+    // exact-parity mode: the reference's optimiser (scipy TRF) restated, km_ik_trf.cuh; one lane, fp64
+    if (g.lane == 0) ik_trf_serial<S, T>(e, b, m, a);
+    g.sync();
+  } else if (feasible) {
     const double lam = 9e-3 * (6e-3 + 2e-6), reg = 9e-3;   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)
     double mu = 0;
     ik_residual<S, T, G>(e, b, m, g, a, b.x, b.r);
@@ -1092,7 +1100,8 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
     const int j = m.arm_mask[a][i];
     const float q = (float)tclip(b.x[i], b.lo[i], b.hi[i]);   // ik_mujoco.py:147-152, then ctrl is float32
     e.ctrl[j] = (T)q;
-    if (feasible && m.ik_teleport) e.qpos[j] = (T)b.x[i];
+    // the reference leaves qpos[mask] at the last point it evaluated (B-1): the solution, or TRF's last trial point
+    if (feasible && m.ik_teleport) e.qpos[j] = (T)(m.ik_mode == 1 ? b.xn[i] : b.x[i]);
   }
   g.sync();
 }

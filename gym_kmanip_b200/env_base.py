@@ -27,7 +27,7 @@ class KManipEnv(GymEnv):
                  act_list: Optional[List[str]] = None, sim: bool = True, mjcf_filename: str = K.SOLO_ARM_MJCF,
                  urdf_filename: str = K.SOLO_ARM_URDF, q_pos_home=None, q_dict=None, q_keys=None, q_id_r_mask=None,
                  q_id_l_mask=None, ctrl_id_r_grip=None, ctrl_id_l_grip=None, log_prefix: str = "test",
-                 log_rerun: bool = False, log_h5py: bool = False, device: int = 0, dtype: str = "float64"):
+                 log_rerun: bool = False, log_h5py: bool = False, device: int = 0, dtype: str = "float64", ik_mode: int = 1):
         super().__init__()
         obs_list = list(obs_list) if obs_list is not None else ["q_pos", "q_vel", "cube_pos", "cube_orn"]
         act_list = list(act_list) if act_list is not None else ["eer_pos", "eer_orn", "grip_r"]
@@ -72,7 +72,8 @@ class KManipEnv(GymEnv):
         # backend seam (env_base.py:192-200)
         self.sim = sim
         from .env_sim import new
-        self.env = new(self, device=device, dtype=dtype)
+        # the single-env class is about fidelity, not throughput: fp64 and the exact-parity IK (restated scipy TRF)
+        self.env = new(self, device=device, dtype=dtype, ik_mode=ik_mode)
         self.info: Dict[str, Any] = {
             "step": self.step_idx, "episode": self.episode_idx, "is_success": False, "q_keys": self.q_keys,
             "q_len": self.q_len, "a_len": self.action_len, "obs_list": self.obs_list, "act_list": self.act_list,

@@ -99,7 +99,7 @@ class _Physics:
 class KManipEnvSim:
     """One simulated env (n = 1) on the GPU with the reference's ``k_*`` protocol."""
 
-    def __init__(self, gym_env, device: int = 0, dtype: str = "float64"):
+    def __init__(self, gym_env, device: int = 0, dtype: str = "float64", ik_mode: int = 1):
         self.gym_env = gym_env
         kwargs = dict(
             mjcf_filename=gym_env.mjcf_filename, q_pos_home=gym_env.q_pos_home, q_id_r_mask=gym_env.q_id_r_mask,
@@ -108,7 +108,7 @@ class KManipEnvSim:
         # truncation is the TimeLimit wrapper's job for the single-env class (reference __init__.py:28,247), so the
         # backend itself never truncates
         self.sim = BatchSim("custom", 1, device=device, dtype=dtype, seed=gym_env.seed, env_kwargs=kwargs,
-                            max_episode_steps=2 ** 30)
+                            max_episode_steps=2 ** 30, ik_mode=ik_mode)
         n_r = 0 if gym_env.q_id_r_mask is None else len(gym_env.q_id_r_mask)
         n_l = 0 if gym_env.q_id_l_mask is None else len(gym_env.q_id_l_mask)
         self._act_layout = action_layout(gym_env.act_list, n_r, n_l)
@@ -149,6 +149,6 @@ class KManipEnvSim:
         self.sim.close()
 
 
-def new(gym_env, device: int = 0, dtype: str = "float64") -> KManipEnvSim:
+def new(gym_env, device: int = 0, dtype: str = "float64", ik_mode: int = 1) -> KManipEnvSim:
     """Factory the env class calls through the backend seam (reference env_base.py:192-196, env_sim.py:206-211)."""
-    return KManipEnvSim(gym_env, device=device, dtype=dtype)
+    return KManipEnvSim(gym_env, device=device, dtype=dtype, ik_mode=ik_mode)

@@ -77,6 +77,7 @@ typedef struct km_task {
   int off_pos[KM_MAXARM], off_orn[KM_MAXARM], off_grip[KM_MAXARM], off_q[KM_MAXARM];
   int cube_body, cube_qposadr;
   int ik_iters, ik_teleport, max_episode_steps;
+  int ik_mode;                           /* 0: fixed-iteration projected LM (fast path); 1: restated scipy TRF (exact-parity mode) */
   double q_home[32], cube_spawn_lo[3], cube_spawn_hi[3];
 } km_task;
 

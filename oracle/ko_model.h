@@ -70,6 +70,7 @@ typedef struct ko_task {
   int ik_iters;              /* damped Gauss-Newton iterations of the device IK */
   int ik_teleport;           /* reproduce ik_mujoco.py:34,67 leaving qpos[mask] at the solution */
   int max_episode_steps;     /* __init__.py:28 */
+  int ik_mode;               /* device IK: 0 fixed-iteration projected LM, 1 restated scipy TRF (the oracle's own "trf" mode calls the real scipy) */
   double q_home[32];         /* float32-rounded home pose, __init__.py:53-122 */
   double cube_spawn_lo[3], cube_spawn_hi[3];   /* __init__.py:164-170 */
 } ko_task;

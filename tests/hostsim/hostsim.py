@@ -19,7 +19,7 @@ from gym_kmanip_b200 import constants as K, flatmodel, mjcf   # noqa: E402
 
 _SO = os.path.join(_HERE, "_build", "libhostsim.so")
 _SRC = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gym_kmanip_b200", "csrc", f) for f in
-                                                ("km_common.cuh", "km_model.cuh", "km_sim.cuh", "km_solver_tpe.cuh", "km_fill.h")]
+                                                ("km_common.cuh", "km_model.cuh", "km_sim.cuh", "km_solver_tpe.cuh", "km_ik_trf.cuh", "km_fill.h")]
 _LIB = None
 SCENE_ID = {"solo_arm": 0, "dual_arm": 1, "torso": 2}
 

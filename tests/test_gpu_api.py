@@ -50,11 +50,12 @@ def test_single_env_follows_the_reference_contract(env_id):
 
 @pytest.mark.gpu
 def test_single_env_matches_oracle_free_running():
-    """The single-env class end to end (dict actions in, dict observations out) against the oracle driven the same
-    way, free-running over one episode from the same spawn (fp64: agreement stays far below contact chaos)."""
+    """The single-env class end to end (dict actions in, dict observations out; fp64, exact-parity IK) against the oracle
+    whose IK is the real scipy TRF, free-running from the same spawn (agreement stays far below contact chaos)."""
+    pytest.importorskip("scipy.optimize")
     from oracle import oracle as om
     env = k.make("KManipSoloArm")
-    o = om.Oracle("KManipSoloArm")
+    o = om.Oracle("KManipSoloArm", ik_mode="trf")
     xyz = np.array([0.22, 0.61, 0.63])
     obs, _ = env.reset(options={"cube_xyz": xyz})
     assert np.allclose(np.concatenate(list(obs.values())), o.reset(xyz), atol=1e-12)

@@ -196,3 +196,42 @@ def test_host_buffer_entry_points_equal_device_entry_points():
     assert h_tr.sum() == 0 and a.launches == b.launches
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id", ["KManipSoloArm", "KManipDualArm"])
+def test_exact_trf_ik_mode_matches_real_scipy(env_id):
+    """ik_mode = 1 (km_ik_trf.cuh on the device) against the oracle whose IK is the REAL scipy.optimize.least_squares,
+    driven per env exactly as the reference does (ik_mujoco.py:129-135): whole env steps, fp64."""
+    pytest.importorskip("scipy.optimize")
+    import torch
+    from gym_kmanip_b200.batch_sim import BatchSim
+    from oracle import oracle as om
+    n, steps = 24, 3
+    o = om.Oracle(env_id, ik_mode="trf")
+    st = om.batch_reset_state(o, n, seed=2)
+    if o.nmocap == 0:
+        st["mocap"] = np.zeros((n, 0))
+    sim = BatchSim(env_id, n, dtype="float64", seed=2, ik_mode=1)
+    rng = np.random.default_rng(8)
+    for t in range(steps):
+        act = rng.uniform(-1, 1, (n, o.task.act_dim)).astype(np.float32)
+        sim.set_state(pack_state(st), step=st["step"], episode=st["episode"])
+        obs, rew, term, trunc = sim.step(torch.from_numpy(act).cuda(), autoreset=False)
+        torch.cuda.synchronize()
+        g = _sim_state(sim)
+        obs_n = obs.cpu().numpy()
+        for i in range(n):
+            o.set_state(st["qpos"][i], st["qvel"][i], st["ctrl"][i], st["warm"][i], st["time"][i], st["mocap"][i] if o.nmocap else None)
+            o_obs, o_rew = o.step(act[i])
+            s = o.get_state()
+            assert rel_err(g["qpos"][i], s["qpos"]) < 1e-9 and rel_err(g["qvel"][i], s["qvel"], floor=1.0) < 1e-8
+            assert np.array_equal(g["ctrl"][i], s["ctrl"])            # float32-rounded on both sides: identical
+            assert rel_err(obs_n[i], o_obs, floor=1.0) < 1e-8
+            for k in ("qpos", "qvel", "ctrl", "warm"):
+                st[k][i] = s[k]
+            st["time"][i] = s["time"]
+            if o.nmocap:
+                st["mocap"][i] = s["mocap"]
+        st["step"] += 1
+    sim.close()
