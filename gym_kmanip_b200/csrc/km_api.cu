@@ -52,8 +52,28 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// threads per CTA of the thread-per-env (local memory) mapping: one CTA per SM holding its share of the batch
+static int tpe_local_threads(const km_sim* h) {
+  const int per_sm = (h->n + h->num_sms - 1) / h->num_sms, cap = h->vt.nv > 16 ? 256 : 128;
+  const int t = (per_sm + 31) / 32 * 32;
+  return t > cap ? cap : t;
+}
+
 static int configure(km_sim* h, int G, int epb) {
   if (G == 0) G = h->G;
+  if (G == 2) {   // thread-per-env with the env record in local memory: epb = threads per CTA (32..256)
+    if (epb == 0) epb = tpe_local_threads(h);
+    if (epb < 1 || epb > 256) return fail(KM_ERR_ARG, "envs_per_block out of range for thread-per-env (local) CTAs");
+    int ctas = 0;
+    KM_CUDA(h->vt.prepare(2, epb, &ctas));
+    if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
+    // one CTA per SM: the records of the resident envs (6.9 KB each for the solo arm) should stay in L2
+    ctas = 1;
+    h->G = 2; h->epb = epb; h->ctas_per_sm = ctas;
+    const long tiles = ((long)h->n + epb - 1) / epb, resident = (long)h->num_sms * ctas;
+    h->grid = (int)(tiles < resident ? tiles : resident);
+    return KM_OK;
+  }
   if (G == 1) {   // thread-per-env: epb = envs (threads) per CTA, bounded by the shared memory one CTA can hold
     const int cap = h->vt.tpe_max_envs;
     if (cap < 1) return fail(KM_ERR_ARG, "an env does not fit in shared memory");
@@ -211,8 +231,17 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
     km_destroy(h);
     return cuda_fail(e, "km_create: initialisation");
   }
-  h->G = 32;   // one env per warp: literal full-warp masks, no divergence between envs sharing a warp
-  int rc = configure(h, h->G, 0);
+  // Default mapping, from the measured grid of profiles/r01_notes.md: the lane-group kernel (one env per warp) while
+  // the batch gives an SM fewer envs than a few warps of threads, the thread-per-env kernel with records in local
+  // memory beyond that (its launch time no longer hangs on single slow envs, and it issues ~7x fewer instructions).
+  const int per_sm = (n_envs + h->num_sms - 1) / h->num_sms;
+  const bool wide = h->vt.nv > 16;                       // dual-arm / torso scenes
+  int rc;
+  if (per_sm >= (wide ? 48 : 96)) rc = configure(h, 2, 0);
+  else {
+    h->G = 32;
+    rc = configure(h, 32, 0);
+  }
   if (rc != KM_OK) { km_destroy(h); return rc; }
   *out = h;
   return KM_OK;
@@ -252,7 +281,8 @@ int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* 
   if (envs_per_block) *envs_per_block = h->epb;
   if (grid) *grid = h->grid;
   if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
-  if (smem_bytes) *smem_bytes = (int)((h->vt.model_bytes + 15) / 16 * 16 + (size_t)h->epb * (h->G == 1 ? h->vt.tpe_env_bytes : h->vt.env_bytes));
+  if (smem_bytes)   // the local-memory mapping (G == 2) keeps only the model tables in shared memory
+    *smem_bytes = (int)((h->vt.model_bytes + 15) / 16 * 16 + (h->G == 2 ? 0 : (size_t)h->epb * (h->G == 1 ? h->vt.tpe_env_bytes : h->vt.env_bytes)));
   return KM_OK;
 }
 

@@ -141,14 +141,17 @@ template <class S, typename T> struct Tpe {
   static constexpr int threads() { return (max_envs() + 31) / 32 * 32; }
   static size_t smem(int epb) { return model_smem<S, T>() + (size_t)epb * stride; }
 };
-template <class S, typename T> __global__ void __launch_bounds__(Tpe<S, T>::threads()) k_env_step_tpe(KmArgs a) {
+// LOCAL: the env record is a local variable (local memory: interleaved across lanes by the hardware, cached in L1/L2)
+// instead of a shared-memory record -- no shared-memory limit on resident warps, at the price of cache-latency accesses.
+template <class S, typename T, bool LOCAL> __global__ void __launch_bounds__(LOCAL ? (Dim<S>::NV > 16 ? 256 : 128) : Tpe<S, T>::threads()) k_env_step_tpe(KmArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   typedef typename Tpe<S, T>::E E;
   const Model<S, T>& m = stage_model<S, T>(smem, a.model);
   Grp<1> g;
   g.lane = 0; g.mask = 1u; g.wmask = 1u;
   if ((int)threadIdx.x >= a.epb) return;          // a CTA may hold fewer envs than its rounded-up warp
-  E& e = *(E*)(smem + model_smem<S, T>() + (size_t)threadIdx.x * Tpe<S, T>::stride);
+  E e_local;
+  E& e = LOCAL ? e_local : *(E*)(smem + model_smem<S, T>() + (size_t)threadIdx.x * Tpe<S, T>::stride);
   init_env<S, T, 1>(e, m, g);
   StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON};
   for (long env = (long)blockIdx.x * a.epb + threadIdx.x; env < a.n; env += (long)gridDim.x * a.epb) {
@@ -230,10 +233,14 @@ template <class S, typename T> struct Launch {
   }
   static cudaError_t dispatch(int which, const KmArgs& a) {
     if (a.G == 1 && which == 0) {
-      k_env_step_tpe<S, T><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), Tpe<S, T>::smem(a.epb), a.stream>>>(a);
+      k_env_step_tpe<S, T, false><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), Tpe<S, T>::smem(a.epb), a.stream>>>(a);
       return cudaGetLastError();
     }
-    if (a.G == 1) {   // reset / contacts are not hot: one env per warp with a small CTA
+    if (a.G == 2 && which == 0) {   // thread per env, record in local memory
+      k_env_step_tpe<S, T, true><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), model_smem<S, T>(), a.stream>>>(a);
+      return cudaGetLastError();
+    }
+    if (a.G == 1 || a.G == 2) {   // reset / contacts are not hot: one env per warp with a small CTA
       KmArgs b = a;
       b.G = 32; b.epb = 4; b.grid = (a.n + 3) / 4 < 148 * 8 ? (a.n + 3) / 4 : 148 * 8;
       return run<32>(which, b);
@@ -264,8 +271,13 @@ template <class S, typename T> struct Launch {
       int dev = 0, optin = 0;
       if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
       if ((err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
-      if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
-      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T>, (epb + 31) / 32 * 32, Tpe<S, T>::smem(epb));
+      if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, false>, (epb + 31) / 32 * 32, Tpe<S, T>::smem(epb));
+    }
+    if (G == 2) {
+      cudaError_t err = prep<32>(4, ctas);
+      if (err != cudaSuccess) return err;
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true>, (epb + 31) / 32 * 32, model_smem<S, T>());
     }
     if (G == 32) return prep<32>(epb, ctas);
     if constexpr (D::NV <= 16) { if (G == 16) return prep<16>(epb, ctas); }

@@ -120,7 +120,9 @@ int km_state_dim(km_handle h);        /* scalars per state record */
 int km_max_contacts(km_handle h);
 int km_num_envs(km_handle h);
 int km_dtype(km_handle h);
-/* launch configuration: lanes per env (16 or 32, at least the dof count) and envs per CTA; 0 keeps the current value */
+/* launch configuration.  lanes_per_env: 32 / 16 = lane group per env (at least the dof count); 1 = thread per env with the
+   env records in shared memory; 2 = thread per env with the records in local memory; 0 keeps the current mapping.
+   envs_per_block: envs per CTA, 0 = choose.  km_create picks a default from the batch size. */
 int km_configure(km_handle h, int lanes_per_env, int envs_per_block);
 long long km_launch_count(km_handle h);   /* kernels launched by this handle so far */
 int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* grid, int* ctas_per_sm, int* smem_bytes);

@@ -6,7 +6,7 @@ uses for the FP-pipe roofline.  The workload is the bench workload: random actio
 averaged over one full episode of 64 envs."""
 import json, os, sys
 import numpy as np
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)   # tests/ -> repo root
 from oracle import oracle as om
 
 out = {}
@@ -26,7 +26,7 @@ for env_id in ["KManipSoloArmQPos", "KManipSoloArm", "KManipDualArm", "KManipDua
         per_step.append((o.flops() - f0) / n)
     out[env_id] = float(np.mean(per_step))
     print(env_id, "FLOP/env-step: mean %.3e  first-steps (free flight) %.3e  late (cube resting) %.3e" % (np.mean(per_step), np.mean(per_step[:5]), np.mean(per_step[-20:])))
-out["note"] = "counted by oracle/kmanip_oracle.cpp -DKO_COUNT_FLOPS over one 64-step episode of 64 envs (tools/count_flops.py); an fma counts as 2"
+out["note"] = "counted by oracle/kmanip_oracle.cpp -DKO_COUNT_FLOPS over one 64-step episode of 64 envs (tests/count_flops.py); an fma counts as 2"
 path = os.path.join(R, "profiles", "flops_per_env_step.json")
 old = {}
 if os.path.exists(path):

@@ -101,13 +101,15 @@ def test_env_step_parity_fp32(env_id):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env_id", ["KManipSoloArm", "KManipDualArm", "KManipTorso", "KManipSoloArmQPos"])
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
-def test_thread_per_env_mapping_parity(env_id, dtype):
-    """The thread-per-env mapping (km_configure(h, 1, 0): k_env_step_tpe with its own Newton solver) against the oracle,
-    same tolerances as the lane-group mapping."""
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_thread_per_env_mapping_parity(env_id, dtype, lanes):
+    """The thread-per-env mapping (k_env_step_tpe with its own Newton solver; km_configure lanes 1: env records in
+    shared memory, lanes 2: in local memory -- the default for large batches) against the oracle, same tolerances as
+    the lane-group mapping."""
     if dtype == "float64":
-        _run(env_id, dtype, n=64, steps=70, tol_pos=1e-10, tol_vel=1e-10, tol_obs=1e-9, lanes=1)
+        _run(env_id, dtype, n=64, steps=70, tol_pos=1e-10, tol_vel=1e-10, tol_obs=1e-9, lanes=lanes)
     else:
-        _run(env_id, dtype, n=64, steps=70, tol_pos=2e-5, tol_vel=1e-4, tol_obs=1e-3, lanes=1)
+        _run(env_id, dtype, n=64, steps=70, tol_pos=2e-5, tol_vel=1e-4, tol_obs=1e-3, lanes=lanes)
 
 
 @pytest.mark.gpu
