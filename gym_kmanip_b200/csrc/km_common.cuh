@@ -124,9 +124,11 @@ template <int G> struct Grp {
 #ifndef KM_LOCKSTEP
 #define KM_LOCKSTEP 2
 #endif
+  // (thread-per-env groups set wmask = ~0u to ask for the phase alignment: there every thread of the CTA runs the
+  // same number of env steps, shadowing a valid env where the batch ends)
   KM_HD void cta_sync() const {
 #if defined(__CUDA_ARCH__)
-    if (G > 1 && KM_LOCKSTEP >= 1) __syncthreads();
+    if (G > 1 ? KM_LOCKSTEP >= 1 : wmask == 0xffffffffu) __syncthreads();
 #endif
   }
   KM_HD bool cta_any(bool p) const {

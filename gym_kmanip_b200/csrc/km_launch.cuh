@@ -143,17 +143,39 @@ template <class S, typename T> struct Tpe {
 };
 // LOCAL: the env record is a local variable (local memory: interleaved across lanes by the hardware, cached in L1/L2)
 // instead of a shared-memory record -- no shared-memory limit on resident warps, at the price of cache-latency accesses.
-template <class S, typename T, bool LOCAL> __global__ void __launch_bounds__(LOCAL ? (Dim<S>::NV > 16 ? 256 : 128) : Tpe<S, T>::threads()) k_env_step_tpe(KmArgs a) {
+// MAXT: largest CTA the instantiation is compiled for (it caps the registers per thread: 255 up to 256 threads, 128 up to 512)
+template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __launch_bounds__(LOCAL ? MAXT : Tpe<S, T>::threads()) k_env_step_tpe(KmArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   typedef typename Tpe<S, T>::E E;
   const Model<S, T>& m = stage_model<S, T>(smem, a.model);
   Grp<1> g;
   g.lane = 0; g.mask = 1u; g.wmask = 1u;
-  if ((int)threadIdx.x >= a.epb) return;          // a CTA may hold fewer envs than its rounded-up warp
+  if (!LOCAL && (int)threadIdx.x >= a.epb) return;          // a CTA may hold fewer envs than its rounded-up warp
   E e_local;
   E& e = LOCAL ? e_local : *(E*)(smem + model_smem<S, T>() + (size_t)threadIdx.x * Tpe<S, T>::stride);
   init_env<S, T, 1>(e, m, g);
   StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON};
+  if (LOCAL) {
+    // Every thread of the CTA walks the same number of tiles, and the warps of the CTA are kept in the same phase of
+    // the sub-step by CTA barriers (the sub-step body is far larger than the instruction cache); threads past the end
+    // of the batch shadow the tile's first env and store nothing.
+    g.wmask = 0xffffffffu;
+    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON};
+    const long tiles = ((long)a.n + a.epb - 1) / a.epb;
+    for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long env = tile * a.epb + threadIdx.x;
+      const bool valid = (int)threadIdx.x < a.epb && env < a.n;
+      const long envc = valid ? env : tile * a.epb;
+      load_state<S, T, 1>(e, a, envc, g);
+      env_step<S, T, 1>(e, m, g, a.act + envc * m.act_dim, valid ? o : none, envc, a.autoreset, a.seed, a.env0);
+      if (valid) {
+        store_state<S, T, 1>(e, a, env, g);
+        if (a.niter) a.niter[env] = e.solver_niter;
+        if (a.ls) a.ls[env] = e.ls_evals;
+      }
+    }
+    return;
+  }
   for (long env = (long)blockIdx.x * a.epb + threadIdx.x; env < a.n; env += (long)gridDim.x * a.epb) {
     load_state<S, T, 1>(e, a, env, g);
 #ifdef KM_TPE_DEBUG
@@ -237,7 +259,8 @@ template <class S, typename T> struct Launch {
       return cudaGetLastError();
     }
     if (a.G == 2 && which == 0) {   // thread per env, record in local memory
-      k_env_step_tpe<S, T, true><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), model_smem<S, T>(), a.stream>>>(a);
+      if (a.epb <= 256) k_env_step_tpe<S, T, true, 256><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), model_smem<S, T>(), a.stream>>>(a);
+      else k_env_step_tpe<S, T, true, 512><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), model_smem<S, T>(), a.stream>>>(a);
       return cudaGetLastError();
     }
     if (a.G == 1 || a.G == 2) {   // reset / contacts are not hot: one env per warp with a small CTA
@@ -277,7 +300,8 @@ template <class S, typename T> struct Launch {
     if (G == 2) {
       cudaError_t err = prep<32>(4, ctas);
       if (err != cudaSuccess) return err;
-      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true>, (epb + 31) / 32 * 32, model_smem<S, T>());
+      if (epb <= 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true, 256>, (epb + 31) / 32 * 32, model_smem<S, T>());
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true, 512>, (epb + 31) / 32 * 32, model_smem<S, T>());
     }
     if (G == 32) return prep<32>(epb, ctas);
     if constexpr (D::NV <= 16) { if (G == 16) return prep<16>(epb, ctas); }
