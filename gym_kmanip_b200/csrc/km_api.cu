@@ -54,11 +54,13 @@ struct DeviceGuard {
 
 // threads per CTA of the thread-per-env (local memory) mapping: one CTA per SM holding its share of the batch
 static int tpe_local_threads(const km_sim* h) {
-  // a single wave of equal CTAs when the batch allows it (measured: 65536 solo-arm envs as 147 CTAs of 448 threads
-  // 6.5e6 env-steps/s, as 256 tiles of 256 threads over 148 CTAs 5.4e6)
-  const int per_sm = (h->n + h->num_sms - 1) / h->num_sms, cap = 512;
-  const int t = (per_sm + 31) / 32 * 32;
-  return t > cap ? cap : t;
+  // equal CTAs in as few full waves as possible (measured: 65536 solo-arm envs as 147 CTAs of 448 threads 6.6e6
+  // env-steps/s, as 256 tiles of 256 threads over 148 CTAs 5.4e6)
+  const long cap = 512, per_wave = (long)h->num_sms * cap;
+  const long waves = ((long)h->n + per_wave - 1) / per_wave;
+  const long per_cta = ((long)h->n + h->num_sms * waves - 1) / (h->num_sms * waves);
+  const long t = (per_cta + 31) / 32 * 32;
+  return (int)(t > cap ? cap : t);
 }
 
 static int configure(km_sim* h, int G, int epb) {

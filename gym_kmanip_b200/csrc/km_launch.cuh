@@ -300,6 +300,9 @@ template <class S, typename T> struct Launch {
     if (G == 2) {
       cudaError_t err = prep<32>(4, ctas);
       if (err != cudaSuccess) return err;
+      // the env records live in local memory: give the unified L1 / shared-memory array to the cache
+      if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T, true, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1)) != cudaSuccess) return err;
+      if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T, true, 512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1)) != cudaSuccess) return err;
       if (epb <= 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true, 256>, (epb + 31) / 32 * 32, model_smem<S, T>());
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true, 512>, (epb + 31) / 32 * 32, model_smem<S, T>());
     }
