@@ -74,3 +74,38 @@ def test_trf_env_step_matches_oracle_with_real_scipy():
         a, b = hs.get_state(), o.get_state()
         assert rel_err(a["qpos"], b["qpos"]) < 1e-6 and rel_err(a["qvel"], b["qvel"], floor=1.0) < 1e-4
         assert rel_err(out["obs"], obs, floor=1.0) < 1e-4
+
+
+def test_out_of_bounds_start_skips_the_solve_like_scipy_raises():
+    """The Torso home pose violates joint limits: scipy raises ValueError for an infeasible x0, the
+    reference swallows it and keeps the current joints (ik_mujoco.py:128-138); both IK modes must do the same."""
+    env_id = "KManipTorso"
+    o = om.Oracle(env_id, ik_mode="trf")
+    st0 = om.batch_reset_state(o, 1, seed=3)
+    qpos = st0["qpos"][0].copy()
+    rngs = np.array(o.flat["jnt_range"])[: o.nu]
+    mask_r = [o.task.arm_mask[0][i] for i in range(o.task.arm_nmask[0])]
+    assert any(qpos[j] < rngs[j, 0] or qpos[j] > rngs[j, 1] for j in range(o.nu)), "home pose expected to violate a limit"
+    st = dict(qpos=qpos, qvel=np.zeros(o.nv), ctrl=qpos[: o.nu].astype(np.float32).astype(np.float64), warm=np.zeros(o.nv),
+              mocap=st0["mocap"][0][: 7 * o.nmocap].copy(), time=0.0)
+    act = np.random.default_rng(1).uniform(-1, 1, o.task.act_dim).astype(np.float32)
+    o.set_state(st["qpos"], st["qvel"], st["ctrl"], st["warm"], 0.0, st["mocap"])
+    o.before_step(act)
+    ref = o.get_state()
+    for mode in (0, 1):
+        hs = hostsim.HostSim(env_id, 64, ik_mode=mode)
+        hs.set_state(st)
+        hs.step1()
+        hs.before_step(act)
+        got = hs.get_state()
+        infeasible = [a for a in range(o.task.n_arm)
+                      if any(qpos[o.task.arm_mask[a][i]] < rngs[o.task.arm_mask[a][i], 0] or qpos[o.task.arm_mask[a][i]] > rngs[o.task.arm_mask[a][i], 1]
+                             for i in range(o.task.arm_nmask[a]))]
+        assert infeasible, "at least one arm starts out of bounds"
+        for a in infeasible:   # that arm: qpos untouched, ctrl = clip(current joints) rounded to float32
+            for i in range(o.task.arm_nmask[a]):
+                j = o.task.arm_mask[a][i]
+                assert got["qpos"][j] == qpos[j]
+                assert got["ctrl"][j] == np.float32(np.clip(qpos[j], rngs[j, 0], rngs[j, 1]))
+        if mode == 1:
+            assert np.abs(got["ctrl"] - ref["ctrl"]).max() < 5e-7 and np.abs(got["qpos"] - ref["qpos"]).max() < 1e-7
