@@ -92,3 +92,18 @@ def test_product_package_never_imports_the_oracle():
     out = subprocess.check_output([sys.executable, "-c", "import sys; import gym_kmanip_b200; "
                                    "print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"], cwd=ROOT)
     assert out.strip() == b"False"
+
+
+def test_error_codes_and_messages_without_a_device():
+    """Argument errors are reported through return codes + km_last_error (no exceptions, no aborts), also with no GPU."""
+    from gym_kmanip_b200 import _lib
+    L = _lib.load()
+    null = C.c_void_p(None)
+    assert L.km_reset(null, None, None, None, None) == -1 and b"null handle" in L.km_last_error()
+    assert L.km_step(null, None, None, 0, None) == -1
+    assert L.km_configure(null, 32, 0) == -1
+    assert L.km_get_state(null, None, None, None, None) == -1
+    assert L.km_site_poses(null, None, None, None) == -1
+    h = C.c_void_p()
+    assert L.km_create(None, None, 0, 4, 0, 32, 0, 0, C.byref(h)) == -1 and b"bad argument" in L.km_last_error()
+    L.km_destroy(null)      # a no-op, must not crash
