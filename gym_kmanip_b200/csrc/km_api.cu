@@ -24,7 +24,7 @@ struct km_sim {
   KmVtable vt;
   int scene, dtype, n, device, act_dim, n_arm;
   unsigned long long seed, env0;
-  int G, epb, grid, ctas_per_sm, num_sms;
+  int G, epb, grid, ctas_per_sm, num_sms, lpw;
   void* d_model;
   void* d_state;
   int *d_step, *d_episode, *d_niter, *d_ls;
@@ -52,24 +52,28 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// threads per CTA of the thread-per-env (local memory) mapping: one CTA per SM holding its share of the batch
-static int tpe_local_threads(const km_sim* h) {
-  // equal CTAs in as few full waves as possible (measured: 65536 solo-arm envs as 147 CTAs of 448 threads 6.6e6
-  // env-steps/s, as 256 tiles of 256 threads over 148 CTAs 5.4e6)
+// envs per CTA of the thread-per-env (local memory) mapping: one CTA per SM holding its share of the batch, equal
+// CTAs in as few full waves as possible (measured: 65536 solo-arm envs as 147 CTAs of 446 envs 6.6e6 env-steps/s, as
+// 256 tiles of 256 over 148 CTAs 5.4e6)
+static int tpe_local_envs(const km_sim* h) {
   const long cap = 512, per_wave = (long)h->num_sms * cap;
   const long waves = ((long)h->n + per_wave - 1) / per_wave;
   const long per_cta = ((long)h->n + h->num_sms * waves - 1) / (h->num_sms * waves);
-  const long t = (per_cta + 31) / 32 * 32;
-  return (int)(t > cap ? cap : t);
+  return (int)(per_cta > cap ? cap : per_cta);
 }
 
 static int configure(km_sim* h, int G, int epb) {
   if (G == 0) G = h->G;
   if (G == 2) {   // thread-per-env with the env record in local memory: epb = threads per CTA (32..256)
-    if (epb == 0) epb = tpe_local_threads(h);
-    if (epb < 1 || epb > 512) return fail(KM_ERR_ARG, "envs_per_block out of range for thread-per-env (local) CTAs");
+    if (epb == 0) epb = tpe_local_envs(h);
+    // Active lanes per warp: all 32.  Dealing the envs of a CTA to more warps with fewer active lanes each was measured
+    // and is far worse (4096 solo-arm envs as 14 warps x 2 lanes per SM: 6.7 ms per launch against 2.7 ms): every
+    // warp executes the whole instruction stream, so issue slots, not latency, become the limit.
+    h->lpw = 32;
+    const int threads = (epb + h->lpw - 1) / h->lpw * 32;
+    if (epb < 1 || threads > 512) return fail(KM_ERR_ARG, "envs_per_block out of range for thread-per-env (local) CTAs");
     int ctas = 0;
-    KM_CUDA(h->vt.prepare(2, epb, &ctas));
+    KM_CUDA(h->vt.prepare(2, threads, &ctas));
     if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
     // one CTA per SM: the records of the resident envs (6.9 KB each for the solo arm) should stay in L2
     ctas = 1;
@@ -130,7 +134,7 @@ static KmArgs base_args(km_sim* h, void* stream) {
   std::memset(&a, 0, sizeof(a));
   a.model = h->d_model; a.state = h->d_state; a.step = h->d_step; a.episode = h->d_episode;
   a.niter = h->d_niter; a.ls = h->d_ls;
-  a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid;
+  a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid; a.lpw = h->lpw > 0 ? h->lpw : 32;
   a.stream = (cudaStream_t)stream;
   return a;
 }
@@ -239,9 +243,9 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   // the batch gives an SM fewer envs than a few warps of threads, the thread-per-env kernel with records in local
   // memory beyond that (its launch time no longer hangs on single slow envs, and it issues ~7x fewer instructions).
   const int per_sm = (n_envs + h->num_sms - 1) / h->num_sms;
-  const bool wide = h->vt.nv > 16;                       // dual-arm / torso scenes
   int rc;
-  if (per_sm >= (wide ? 48 : 96)) rc = configure(h, 2, 0);
+  const int tpe_from = h->vt.nv > 16 ? 48 : 96;   // envs per SM from which the thread-per-env kernel wins (dual-arm / torso: 48)
+  if (per_sm >= tpe_from) rc = configure(h, 2, 0);
   else {
     h->G = 32;
     rc = configure(h, 32, 0);

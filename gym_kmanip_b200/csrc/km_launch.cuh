@@ -35,6 +35,7 @@ struct KmArgs {
   int n, autoreset;
   unsigned long long seed, env0;
   int G, epb, grid;
+  int lpw;   // thread-per-env (local) mapping: active lanes per warp (envs of a CTA are spread over its warps)
   cudaStream_t stream;
 };
 
@@ -163,8 +164,11 @@ template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __lau
     const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON};
     const long tiles = ((long)a.n + a.epb - 1) / a.epb;
     for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const long env = tile * a.epb + threadIdx.x;
-      const bool valid = (int)threadIdx.x < a.epb && env < a.n;
+      // envs of the tile are dealt to the warps lpw at a time: with few envs per SM every scheduler still gets a
+      // warp, and a warp only waits for the slowest of its own lpw envs
+      const int lane = threadIdx.x & 31, slot = (threadIdx.x >> 5) * a.lpw + lane;
+      const long env = tile * a.epb + slot;
+      const bool valid = lane < a.lpw && slot < a.epb && env < a.n;
       const long envc = valid ? env : tile * a.epb;
       load_state<S, T, 1>(e, a, envc, g);
       env_step<S, T, 1>(e, m, g, a.act + envc * m.act_dim, valid ? o : none, envc, a.autoreset, a.seed, a.env0);
@@ -259,8 +263,9 @@ template <class S, typename T> struct Launch {
       return cudaGetLastError();
     }
     if (a.G == 2 && which == 0) {   // thread per env, record in local memory
-      if (a.epb <= 256) k_env_step_tpe<S, T, true, 256><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), model_smem<S, T>(), a.stream>>>(a);
-      else k_env_step_tpe<S, T, true, 512><<<dim3(a.grid), dim3((a.epb + 31) / 32 * 32), model_smem<S, T>(), a.stream>>>(a);
+      const int threads = (a.epb + a.lpw - 1) / a.lpw * 32;   // warps needed to hold epb envs at lpw active lanes each
+      if (threads <= 256) k_env_step_tpe<S, T, true, 256><<<dim3(a.grid), dim3(threads), model_smem<S, T>(), a.stream>>>(a);
+      else k_env_step_tpe<S, T, true, 512><<<dim3(a.grid), dim3(threads), model_smem<S, T>(), a.stream>>>(a);
       return cudaGetLastError();
     }
     if (a.G == 1 || a.G == 2) {   // reset / contacts are not hot: one env per warp with a small CTA

@@ -98,15 +98,18 @@ def test_vector_env_autoreset_and_totals():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env_id,n", [("KManipSoloArmQPos", 4096), ("KManipSoloArm", 8192)])
-def test_properties_at_baseline_batch_sizes(env_id, n):
+@pytest.mark.parametrize("lanes", [32, 2])
+def test_properties_at_baseline_batch_sizes(env_id, n, lanes):
     """Size-independent properties at the BASELINE.json batch sizes: bit-exact determinism, independence from how envs
-    are sharded into handles (global env ids), unit quaternions, observation bounds, truncation every 64 steps."""
+    are sharded into handles (global env ids; same kernel mapping on every shard -- km_create would pick the mapping
+    from each shard's own size), unit quaternions, observation bounds, truncation every 64 steps."""
     import torch
     from gym_kmanip_b200.batch_sim import BatchSim
     whole = BatchSim(env_id, n, dtype="float32", seed=9)
     again = BatchSim(env_id, n, dtype="float32", seed=9)
     half = [BatchSim(env_id, n // 2, dtype="float32", seed=9, env0=0), BatchSim(env_id, n // 2, dtype="float32", seed=9, env0=n // 2)]
     for s in [whole, again] + half:
+        s.configure(lanes, 0)
         s.reset()
     gen = torch.Generator(device="cuda").manual_seed(3)
     ntrunc = 0
@@ -124,4 +127,29 @@ def test_properties_at_baseline_batch_sizes(env_id, n):
         assert float((quat.norm(dim=1) - 1).abs().max()) < 1e-5
     assert ntrunc == n
     for s in [whole, again] + half:
+        s.close()
+
+
+@pytest.mark.gpu
+def test_mappings_agree_with_each_other():
+    """The three kernel mappings (lane group, thread per env in shared / local memory) are the same simulator: from
+    the same state and action they agree to fp32 rounding."""
+    import torch
+    from gym_kmanip_b200.batch_sim import BatchSim
+    n = 512
+    sims = []
+    for lanes in (32, 1, 2):
+        s = BatchSim("KManipSoloArm", n, dtype="float32", seed=4)
+        s.configure(lanes, 0)
+        s.reset()
+        sims.append(s)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(6):
+        act = torch.rand(n, sims[0].act_dim, device="cuda", generator=gen) * 2 - 1
+        outs = [s.step(act, autoreset=True)[0].clone() for s in sims]
+        st0 = sims[0].get_state()[0]
+        for s, o in zip(sims[1:], outs[1:]):
+            assert float((o - outs[0]).abs().max()) < 2e-3          # q_vel / pi entries carry ~100 rad/s velocities
+            s.set_state(st0)                                          # teacher-force: keep the comparison per step
+    for s in sims:
         s.close()

@@ -5,7 +5,9 @@ import torch
 from gym_kmanip_b200.batch_sim import BatchSim
 env = sys.argv[1] if len(sys.argv) > 1 else "KManipSoloArmQPos"
 n = 4096
-sim = BatchSim(env, n, dtype="float32", seed=1)
+dtype = sys.argv[2] if len(sys.argv) > 2 else "float32"
+sim = BatchSim(env, n, dtype=dtype, seed=1)
+sim.configure(32, 0)
 sim.reset()
 gen = torch.Generator(device="cuda").manual_seed(0)
 for t in range(64):
