@@ -44,11 +44,13 @@ def parse():
     p.add_argument("--epb", type=int, default=0)
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--ik-mode", type=int, default=0, help="0: fast fixed-iteration LM IK (default of the batched path); 1: exact-parity scipy-TRF restatement")
     return p.parse_args()
 
 
 def workload_name(a):
-    return f"{a.env}, {a.envs} envs/GPU, random actions, autoreset every 64 steps, {a.dtype}"
+    ik = ", exact-parity TRF IK" if getattr(a, "ik_mode", 0) == 1 else ""
+    return f"{a.env}, {a.envs} envs/GPU, random actions, autoreset every 64 steps, {a.dtype}{ik}"
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle port)
@@ -148,7 +150,7 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = a.envs
-    sim = BatchSim(a.env, n, device=local, dtype=a.dtype, seed=0, env0=rank * n)
+    sim = BatchSim(a.env, n, device=local, dtype=a.dtype, seed=0, env0=rank * n, ik_mode=a.ik_mode)
     if a.lanes or a.epb:
         sim.configure(a.lanes, a.epb)
     cfg = sim.launch_config()

@@ -10,8 +10,10 @@
 //                                      make_strictly_feasible, find_active_constraints
 //     scipy/optimize/_lsq/least_squares.py  (x0 made strictly feasible, ValueError when x0 is out of bounds)
 // with one substitution that is exact in exact arithmetic: instead of the SVD of the (m+n) x n augmented Jacobian it
-// uses the symmetric eigen-decomposition (cyclic Jacobi) of the n x n matrix A = J_h^T J_h + diag(diag_h), whose
-// eigenvalues are the squared singular values, whose eigenvectors are V, and for which s * (U^T f_aug) = V^T g_h.
+// uses the n x n matrix A = J_h^T J_h + diag(diag_h): its Cholesky factor for the Gauss-Newton step (what the
+// trust-region solver returns whenever that step lies inside the region), and otherwise its symmetric
+// eigen-decomposition (cyclic Jacobi), whose eigenvalues are the squared singular values, whose eigenvectors are V,
+// and for which s * (U^T f_aug) = V^T g_h.
 // Parity against the real scipy is checked by tests/test_ik_trf.py (host build of this file, fp64) and on the GPU.
 //
 // Everything is fp64 and serial: one lane runs it (n <= 8 unknowns); it is the parity mode, not the fast path
@@ -260,19 +262,51 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
         Bh[i][j] = d[i] * JtJ[i][j] * d[j];
         Aw[i][j] = Bh[i][j] + (i == j ? diag_h[i] : 0.0);
       }
-    eig_sym(Aw, n, w, V);
-    for (int i = 0; i < n; i++) {
-      s[i] = N::sqrt(tmax(w[i], 0.0));
-      double r = 0;
-      for (int k = 0; k < n; k++) r += V[k][i] * g_h[k];
-      suf[i] = r;
+    // Gauss-Newton step p = -A^{-1} g_h by Cholesky.  When A is safely positive definite and the step lies inside the
+    // trust region this is what solve_lsq_trust_region returns (full-rank branch, alpha = 0) and the eigen-decomposition
+    // is never needed; otherwise (trust region active, or A close to singular) the decomposition is computed lazily.
+    double p_gn[NMAX], Lc[NMAX][NMAX];
+    bool gn_ok = true, have_eig = false;
+    {
+      double dmax = 0;
+      for (int i = 0; i < n; i++) dmax = tmax(dmax, Aw[i][i]);
+      for (int j = 0; j < n && gn_ok; j++) {
+        double dj = Aw[j][j];
+        for (int k = 0; k < j; k++) dj -= Lc[j][k] * Lc[j][k];
+        if (!(dj > 1e-10 * dmax)) { gn_ok = false; break; }      // far above the EPS * m * s_max rank threshold of scipy
+        Lc[j][j] = N::sqrt(dj);
+        for (int i = j + 1; i < n; i++) {
+          double sacc = Aw[i][j];
+          for (int k = 0; k < j; k++) sacc -= Lc[i][k] * Lc[j][k];
+          Lc[i][j] = sacc / Lc[j][j];
+        }
+      }
+      if (gn_ok) {
+        for (int i = 0; i < n; i++) { double t = -g_h[i]; for (int k = 0; k < i; k++) t -= Lc[i][k] * p_gn[k]; p_gn[i] = t / Lc[i][i]; }
+        for (int i = n - 1; i >= 0; i--) { double t = p_gn[i]; for (int k = i + 1; k < n; k++) t -= Lc[k][i] * p_gn[k]; p_gn[i] = t / Lc[i][i]; }
+      }
     }
     const double theta = tmax(0.995, 1.0 - g_norm);
     double actual_reduction = -1.0, cost_new = cost;
     double x_new[NMAX], f_new[6 + 2 * NMAX];
     while (actual_reduction <= 0.0 && nfev < max_nfev) {
       double p_h[NMAX], p[NMAX], step[NMAX], step_h[NMAX], predicted;
-      solve_lsq_trust_region(n, mres, suf, s, V, Delta, &alpha, p_h);
+      if (gn_ok && norm(p_gn, n) <= Delta) {
+        for (int i = 0; i < n; i++) p_h[i] = p_gn[i];
+        alpha = 0.0;
+      } else {
+        if (!have_eig) {
+          have_eig = true;
+          eig_sym(Aw, n, w, V);
+          for (int i = 0; i < n; i++) {
+            s[i] = N::sqrt(tmax(w[i], 0.0));
+            double r = 0;
+            for (int k = 0; k < n; k++) r += V[k][i] * g_h[k];
+            suf[i] = r;
+          }
+        }
+        solve_lsq_trust_region(n, mres, suf, s, V, Delta, &alpha, p_h);
+      }
       for (int i = 0; i < n; i++) p[i] = d[i] * p_h[i];
       // ---- trf.py: select_step
       {
