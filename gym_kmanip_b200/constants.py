@@ -6,6 +6,7 @@ reward weights, home poses, index masks) and the kwargs of its eight ``register(
 """
 from __future__ import annotations
 
+import os as _os
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
@@ -19,6 +20,8 @@ SOLO_ARM_URDF = "stompy_tiny_solo_arm_glb.urdf"
 DUAL_ARM_URDF = "stompy_dual_arm_tiny_glb.urdf"
 TORSO_URDF = "stompy_tiny_glb/robot.urdf"
 
+DATA_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "data")   # reference __init__.py:12
+DATE_FORMAT = "%mm%dd%Yy_%Hh%Mm"   # :15
 MAX_EPISODE_STEPS = 64            # reference __init__.py:28
 FPS = 30                          # :29
 CONTROL_TIMESTEP = 0.02           # :30

@@ -5,11 +5,12 @@ observation / action spaces (float64 observations in [-1, 1], float32 actions in
 ``reset`` -> ``(obs, info)``, ``step`` -> ``(obs, reward, terminated, False, info)`` with ``is_success = reward > 2``.
 The backend is selected through the same seam (``self.env = new(self)``), bound to the CUDA backend of
 env_sim.py.  ``make(id)`` applies the 64-step TimeLimit that ``gym.make`` adds from the registration
-(reference __init__.py:28,247).  Loggers (h5py / rerun), the real-robot backend and camera observations are outside
-the accelerated path and raise NotImplementedError when requested.
+(reference __init__.py:28,247).  ``log_h5py=True`` writes per-episode files in the reference's layout (log_episode.py);
+the rerun logger, the real-robot backend and camera observations are out of scope and raise NotImplementedError.
 """
 from __future__ import annotations
 
+import os
 import time
 from collections import OrderedDict
 from typing import Any, Dict, List, Optional
@@ -31,8 +32,8 @@ class KManipEnv(GymEnv):
         super().__init__()
         obs_list = list(obs_list) if obs_list is not None else ["q_pos", "q_vel", "cube_pos", "cube_orn"]
         act_list = list(act_list) if act_list is not None else ["eer_pos", "eer_orn", "grip_r"]
-        if log_rerun or log_h5py:
-            raise NotImplementedError("episode loggers are outside the accelerated hot path (SURVEY.md 8f rank 3)")
+        if log_rerun:
+            raise NotImplementedError("the rerun visualisation logger is out of scope (SURVEY.md 2.1 #8)")
         if not sim:
             raise NotImplementedError("the real-robot backend is out of scope (SURVEY.md 2.1 #6)")
         if any("camera" in o for o in obs_list):
@@ -49,7 +50,14 @@ class KManipEnv(GymEnv):
         self.q_id_r_mask, self.q_id_l_mask = q_id_r_mask, q_id_l_mask
         self.ctrl_id_r_grip, self.ctrl_id_l_grip = ctrl_id_r_grip, ctrl_id_l_grip
         self.cameras: list = []
-        self.log_rerun, self.log_h5py = False, False
+        self.log_rerun, self.log_h5py = False, bool(log_h5py)
+        self._log = None
+        if self.log_h5py:   # per-episode files in the reference's layout (env_base.py:82-95, log_h5py.py)
+            import uuid
+            from datetime import datetime
+            name = "{}.{}.{}".format(log_prefix, str(uuid.uuid4())[:6], datetime.now().strftime(K.DATE_FORMAT))
+            self.log_dir = os.path.join(K.DATA_DIR, name)
+            os.makedirs(self.log_dir, exist_ok=True)
         self.mjcf_filename, self.urdf_filename = mjcf_filename, urdf_filename
         # observation space (env_base.py:116-147)
         self.obs_list = obs_list
@@ -99,15 +107,24 @@ class KManipEnv(GymEnv):
         self.step_idx = 0
         self.episode_idx += 1
         self._stamp(sim_time, reward, terminated, False)
+        if self.log_h5py:
+            from . import log_episode
+            log_episode.end(self._log)
+            self._log = log_episode.new(self.log_dir, self.info)
         return observation, self.info
 
     def step(self, action):
         terminated, reward, _, observation, sim_time = self.env.k_step(action)
         self.step_idx += 1
         self._stamp(sim_time, reward, terminated, reward > K.REWARD_SUCCESS_THRESHOLD)
+        if self._log is not None and self.step_idx <= K.MAX_EPISODE_STEPS:
+            self._log.step(action, observation, self.info)
         return observation, reward, terminated, False, self.info
 
     def close(self):
+        if self._log is not None:
+            self._log.end()
+            self._log = None
         self.env.k_close()
         super().close()
 

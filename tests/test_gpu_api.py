@@ -1,6 +1,8 @@
 """GPU: the reference-facing Python API (KManipEnv / make, KManipVectorEnv) and size-independent properties of the
 CUDA path at BASELINE.json's batch sizes.  The API checks restate what gymnasium's check_env pins for the reference
 (tests/test_env.py:8-24: spaces, dtypes, bounds, 5-tuple types), plus the TimeLimit truncation of gym.make."""
+import os
+
 import numpy as np
 import pytest
 
@@ -153,3 +155,25 @@ def test_mappings_agree_with_each_other():
             s.set_state(st0)                                          # teacher-force: keep the comparison per step
     for s in sims:
         s.close()
+
+
+@pytest.mark.gpu
+def test_single_env_episode_logging(tmp_path, monkeypatch):
+    """log_h5py=True (reference examples/2_log_with_h5py.py): one file per episode under log_dir, reference layout."""
+    from gym_kmanip_b200 import constants as K
+    monkeypatch.setattr(K, "DATA_DIR", str(tmp_path))
+    env = k.make("KManipSoloArm", log_h5py=True, ik_mode=0)
+    u = env.unwrapped
+    u.action_space.seed(0)
+    env.reset()
+    for _ in range(5):
+        env.step(u.action_space.sample())
+    env.reset()
+    env.step(u.action_space.sample())
+    env.close()
+    files = sorted(os.listdir(u.log_dir))
+    assert [f.split(".")[0] for f in files] == ["episode_1", "episode_2"]
+    if files[0].endswith(".npz"):
+        d = np.load(os.path.join(u.log_dir, files[0]))
+        assert d["observations/qpos"].shape == (64, 10) and d["action"].shape == (64, 3)
+        assert d["observations/qpos"][:5].any() and not d["observations/qpos"][5:].any()

@@ -1,5 +1,8 @@
 """CPU: host-side logic of the drop-in boundary -- registry, spaces, flat action / observation layouts, task structs,
 env sharding -- mirroring what gymnasium's check_env pins for the reference (tests/test_env.py:8-24)."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -79,6 +82,41 @@ def test_vision_ids_and_loggers_are_declared_out_of_scope():
     with pytest.raises(NotImplementedError):
         KManipEnv(**K.ENV_REGISTRY["KManipSoloArmVision"])
     with pytest.raises(NotImplementedError):
-        KManipEnv(**dict(K.ENV_REGISTRY["KManipSoloArm"], log_h5py=True))
+        KManipEnv(**dict(K.ENV_REGISTRY["KManipSoloArm"], log_rerun=True))
     with pytest.raises(KeyError):
         k.make("KManipNope")
+
+
+def test_episode_log_layout_follows_the_reference(tmp_path):
+    """log_episode writes the reference's ACT layout (log_h5py.py:13-61), quirks included: the logged qpos / qvel are
+    the normalised observations and every action row is grip_r broadcast over a_len columns."""
+    from gym_kmanip_b200 import log_episode
+    info = {"step": 0, "episode": 3, "is_success": False, "q_keys": ["a", "b"], "q_len": 10, "a_len": 3, "obs_list": ["q_pos"],
+            "act_list": ["eer_pos", "eer_orn", "grip_r"], "cameras": [], "sim": True, "cpu_time": 1.0, "reward": None}
+    f = log_episode.new(str(tmp_path), info)
+    rng = np.random.default_rng(0)
+    rows = []
+    for t in range(1, 6):
+        info["step"] = t
+        act = {"eer_pos": rng.uniform(-1, 1, 3).astype(np.float32), "eer_orn": rng.uniform(-1, 1, 3).astype(np.float32),
+               "grip_r": rng.uniform(-1, 1, 1).astype(np.float32)}
+        obs = {"q_pos": rng.uniform(0, 1, 10), "q_vel": rng.uniform(-1, 1, 10)}
+        log_episode.step(f, act, obs, info)
+        rows.append((act, obs))
+    path = log_episode.end(f)
+    assert os.path.basename(path).startswith("episode_3.")
+    if path.endswith(".npz"):
+        d = np.load(path)
+        qpos, qvel, action = d["observations/qpos"], d["observations/qvel"], d["action"]
+        attrs = json.loads(str(d["__attrs__"]))
+        assert attrs["sim"] is True and attrs["metadata"]["q_len"] == 10 and attrs["metadata"]["episode"] == 3
+    else:                                  # pragma: no cover - h5py present
+        import h5py
+        with h5py.File(path) as d:
+            qpos, qvel, action = d["observations/qpos"][:], d["observations/qvel"][:], d["action"][:]
+            assert d.attrs["sim"] and d["metadata"].attrs["q_len"] == 10
+    assert qpos.shape == (64, 10) and qvel.shape == (64, 10) and action.shape == (64, 3)
+    for t, (act, obs) in enumerate(rows):
+        assert np.allclose(qpos[t], obs["q_pos"], atol=1e-7) and np.allclose(qvel[t], obs["q_vel"], atol=1e-7)
+        assert np.all(action[t] == act["grip_r"][0])
+    assert not qpos[5:].any()
