@@ -86,3 +86,74 @@ def step(f: EpisodeLog, action, observation, info) -> None:
 
 def end(f: EpisodeLog):
     return None if f is None else f.end()
+
+
+class BatchEpisodeLog:
+    """Episode logger of the batched env: device ring buffers, one file per finished episode of each logged env.
+
+    ``KManipVectorEnv(..., log_dir=..., log_env_ids=[...])`` feeds it every step.  Each logged env owns one column of
+    three ring buffers on the device (``q_pos`` / ``q_vel`` observations and the ``grip_r`` command, MAX_EPISODE_STEPS
+    rows, float32 -- the arrays of reference log_h5py.py:27-43); a step appends one row per env with a single indexed
+    store and nothing leaves the device until an env's episode ends (truncation), when that env's rows are copied to the
+    host and written with the same dataset names, quirks and zero padding as the single-env logger above.  Files are
+    named ``env<global id>_episode_<k>`` (the reference has one env, hence ``episode_<k>``).
+    """
+
+    def __init__(self, log_dir: str, env_ids, q_len: int, a_len: int, grip_col: int, torch, device, env0: int = 0,
+                 info: Dict[str, Any] = None, max_steps: int = K.MAX_EPISODE_STEPS):
+        assert os.path.exists(log_dir), f"Directory {log_dir} does not exist"
+        t = self.torch = torch
+        self.log_dir, self.q_len, self.a_len, self.grip_col, self.env0 = log_dir, int(q_len), int(a_len), int(grip_col), int(env0)
+        self.max_steps = int(max_steps)
+        self.ids = t.as_tensor(list(env_ids), dtype=t.long, device=device)
+        n = self.ids.numel()
+        self.cols = t.arange(n, device=device)
+        self.qpos = t.zeros(self.max_steps, n, self.q_len, dtype=t.float32, device=device)
+        self.qvel = t.zeros(self.max_steps, n, self.q_len, dtype=t.float32, device=device)
+        self.grip = t.zeros(self.max_steps, n, dtype=t.float32, device=device)
+        self.row = t.zeros(n, dtype=t.long, device=device)          # next free row of each column
+        self.episode = [1] * n
+        self.info = dict(info or {})
+        self.paths = []
+
+    def step(self, act_flat, obs_flat, final_obs_flat, done) -> int:
+        """Append this step (the finished episode's last observation comes from ``final_obs_flat``); returns files written."""
+        t = self.torch
+        d = done[self.ids].bool()
+        obs = t.where(d[:, None], final_obs_flat[self.ids], obs_flat[self.ids]).to(t.float32)
+        r = self.row.clamp(max=self.max_steps - 1)
+        keep = self.row < self.max_steps                             # the reference stops logging past MAX_EPISODE_STEPS
+        rk, ck = r[keep], self.cols[keep]
+        self.qpos[rk, ck] = obs[keep, :self.q_len]
+        self.qvel[rk, ck] = obs[keep, self.q_len:2 * self.q_len]
+        self.grip[rk, ck] = act_flat[self.ids, self.grip_col].to(t.float32)[keep]
+        self.row += 1
+        if not bool(d.any()):                                        # one flag read per step; rows stay on the device
+            return 0
+        cols = t.nonzero(d).flatten()
+        qpos, qvel, grip = self.qpos[:, cols].cpu().numpy(), self.qvel[:, cols].cpu().numpy(), self.grip[:, cols].cpu().numpy()
+        rows = self.row[cols].cpu().numpy()
+        for k, c in enumerate(cols.tolist()):
+            gid = self.env0 + int(self.ids[c])
+            meta = dict(self.info, env=gid, episode=self.episode[c], step=int(rows[k]), q_len=self.q_len, a_len=self.a_len, sim=True)
+            f = EpisodeLog.__new__(EpisodeLog)
+            f.q_len, f.a_len, f.attrs, f.path = self.q_len, self.a_len, {"sim": True}, None
+            f.stem = os.path.join(self.log_dir, f"env{gid:06d}_episode_{self.episode[c]}")
+            f.metadata = {key: v for key, v in meta.items() if _jsonable(v)}
+            f.qpos, f.qvel = qpos[:, k], qvel[:, k]
+            f.action = np.repeat(grip[:, k, None], self.a_len, axis=1)   # grip_r broadcast over a_len columns (log_h5py.py:55)
+            self.paths.append(f.end())
+            self.episode[c] += 1
+        self.qpos[:, cols] = 0
+        self.qvel[:, cols] = 0
+        self.grip[:, cols] = 0
+        self.row[cols] = 0
+        return len(cols)
+
+
+def _jsonable(v) -> bool:
+    try:
+        json.dumps(v)
+        return True
+    except TypeError:
+        return False

@@ -21,7 +21,7 @@ from .spaces import Box, Dict as DictSpace
 
 class KManipVectorEnv:
     def __init__(self, env_id: str, num_envs: int, device: int = 0, dtype: str = "float32", seed: int = 0, env0: int = 0,
-                 max_episode_steps: int = K.MAX_EPISODE_STEPS, **sim_kwargs):
+                 max_episode_steps: int = K.MAX_EPISODE_STEPS, log_dir: Optional[str] = None, log_env_ids=None, **sim_kwargs):
         kw = K.ENV_REGISTRY[env_id]
         if any("camera" in o for o in kw["obs_list"]):
             raise NotImplementedError("camera observations are outside the accelerated hot path (SURVEY.md 8f rank 4)")
@@ -43,6 +43,14 @@ class KManipVectorEnv:
         self.episode_return = t.zeros(self.num_envs, dtype=t.float64, device=self.device)
         # running totals of the rollout: sum of rewards, env steps, finished episodes, success steps
         self.totals = t.zeros(4, dtype=t.float64, device=self.device)
+        # episode logger (reference log_h5py.py) fed from device ring buffers; log_env_ids: local env indices (default: env 0)
+        self.log = None
+        if log_dir is not None:
+            from .log_episode import BatchEpisodeLog
+            ids = [0] if log_env_ids is None else list(log_env_ids)
+            self.log = BatchEpisodeLog(log_dir, ids, self.sim.q_len, len(self.action_layout), self.action_layout["grip_r"].start,
+                                       t, self.device, env0=env0, max_steps=max_episode_steps,
+                                       info={"env_id": env_id, "obs_list": self.obs_list, "act_list": self.act_list})
 
     # -------------------------------------------------------------------------------- helpers
     def _obs_dict(self, flat) -> "OrderedDict[str, object]":
@@ -75,7 +83,10 @@ class KManipVectorEnv:
 
     def step(self, action):
         t = self.sim.torch
-        flat, rew, term, trunc = self.sim.step(self.flatten_action(action), autoreset=True)
+        act = self.flatten_action(action)
+        flat, rew, term, trunc = self.sim.step(act, autoreset=True)
+        if self.log is not None:
+            self.log.step(act, flat, self.sim.final_obs, trunc)
         success = rew > K.REWARD_SUCCESS_THRESHOLD                   # env_base.py:249
         done = trunc.bool()
         self.episode_return += rew.double()

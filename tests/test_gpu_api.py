@@ -177,3 +177,27 @@ def test_single_env_episode_logging(tmp_path, monkeypatch):
         d = np.load(os.path.join(u.log_dir, files[0]))
         assert d["observations/qpos"].shape == (64, 10) and d["action"].shape == (64, 3)
         assert d["observations/qpos"][:5].any() and not d["observations/qpos"][5:].any()
+
+
+@pytest.mark.gpu
+def test_vector_env_episode_logging_from_device_ring_buffers(tmp_path):
+    """KManipVectorEnv(log_dir=...): logged envs' rows stay on the device until truncation, then one file per episode."""
+    import torch
+    env = KManipVectorEnv("KManipSoloArmQPos", 64, seed=3, max_episode_steps=4, log_dir=str(tmp_path), log_env_ids=[0, 63])
+    obs, _ = env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rows = []
+    for t in range(9):
+        act = env.sample_actions(g)
+        obs, rew, term, trunc, info = env.step(act)
+        src = torch.where(trunc.bool()[:, None], env.sim.final_obs, env.sim.obs)
+        rows.append((act[63, 7].item(), src[63, :10].float().cpu().numpy()))
+    files = sorted(os.listdir(tmp_path))
+    assert [f.split(".")[0] for f in files] == ["env000000_episode_1", "env000000_episode_2", "env000063_episode_1", "env000063_episode_2"]
+    if files[-1].endswith(".npz"):
+        d = np.load(os.path.join(tmp_path, files[-1]))
+        assert d["observations/qpos"].shape == (64, 10) and d["action"].shape == (64, 2)
+        for r in range(4):
+            assert np.allclose(d["observations/qpos"][r], rows[4 + r][1], atol=1e-7) and np.all(d["action"][r] == np.float32(rows[4 + r][0]))
+        assert not d["observations/qpos"][4:].any()
+    env.close()

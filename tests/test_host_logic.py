@@ -120,3 +120,40 @@ def test_episode_log_layout_follows_the_reference(tmp_path):
         assert np.allclose(qpos[t], obs["q_pos"], atol=1e-7) and np.allclose(qvel[t], obs["q_vel"], atol=1e-7)
         assert np.all(action[t] == act["grip_r"][0])
     assert not qpos[5:].any()
+
+
+def test_batch_episode_log_ring_buffers(tmp_path):
+    """BatchEpisodeLog: ring buffers (here CPU tensors; CUDA tensors in the batched env) -> one file per finished
+    episode of each logged env, same layout and quirks as the single-env logger; the finished episode's last row is the
+    final observation, not the first observation of the next episode."""
+    import torch
+    from gym_kmanip_b200.log_episode import BatchEpisodeLog
+    n, q_len, act_dim, T = 6, 10, 7, 4
+    log = BatchEpisodeLog(str(tmp_path), [1, 4], q_len, 3, 6, torch, "cpu", env0=100, max_steps=64, info={"env_id": "KManipSoloArm"})
+    g = torch.Generator().manual_seed(0)
+    hist = []
+    for t in range(2 * T + 1):
+        act = torch.rand(n, act_dim, generator=g) * 2 - 1
+        obs, fin = torch.rand(n, 27, generator=g, dtype=torch.float64), torch.rand(n, 27, generator=g, dtype=torch.float64)
+        done = torch.zeros(n, dtype=torch.uint8)
+        if (t + 1) % T == 0:
+            done[:] = 1
+        wrote = log.step(act, obs, fin, done)
+        assert wrote == (2 if done[0] else 0)
+        hist.append((act, obs, fin, done))
+    names = sorted(os.path.basename(p).split(".")[0] for p in log.paths)
+    assert names == ["env000101_episode_1", "env000101_episode_2", "env000104_episode_1", "env000104_episode_2"]
+    path = [p for p in log.paths if "env000104_episode_2" in p][0]
+    if path.endswith(".npz"):
+        d = np.load(path)
+        qpos, qvel, action = d["observations/qpos"], d["observations/qvel"], d["action"]
+        meta = json.loads(str(d["__attrs__"]))["metadata"]
+        assert meta["env"] == 104 and meta["episode"] == 2 and meta["step"] == T and meta["env_id"] == "KManipSoloArm"
+        assert qpos.shape == (64, q_len) and action.shape == (64, 3)
+        for r in range(T):
+            act, obs, fin, done = hist[T + r]
+            src = fin if done[4] else obs
+            assert np.allclose(qpos[r], src[4, :q_len].numpy(), atol=1e-7) and np.allclose(qvel[r], src[4, q_len:2 * q_len].numpy(), atol=1e-7)
+            assert np.all(action[r] == act[4, 6].numpy())
+        assert not qpos[T:].any() and not action[T:].any()
+    assert int(log.row[0]) == 1 and log.qpos[1:].abs().sum() == 0   # the ninth step opened episode 3

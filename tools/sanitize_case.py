@@ -1,0 +1,17 @@
+"""Small case for compute-sanitizer: every mapping, a few env steps with autoreset, reset, contacts, site poses."""
+import sys, os
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
+import torch
+from gym_kmanip_b200.batch_sim import BatchSim
+for env in ("KManipSoloArm", "KManipDualArm"):
+    for lanes in (32, 1, 2):
+        s = BatchSim(env, 40, dtype="float32", seed=1, max_episode_steps=3)
+        s.configure(lanes, 0)
+        s.reset()
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        for t in range(5):
+            s.step(torch.rand(40, s.act_dim, device="cuda", generator=gen) * 2 - 1, autoreset=True)
+        s.contacts(); s.site_poses(); s.get_state()
+        torch.cuda.synchronize()
+        s.close()
+        print(env, lanes, "ok", flush=True)
