@@ -18,6 +18,7 @@ EXPORTS = [
     "km_act_dim", "km_state_dim", "km_max_contacts", "km_num_envs", "km_dtype", "km_configure", "km_launch_count",
     "km_launch_config", "km_reset", "km_step", "km_get_state", "km_set_state", "km_state_ptr", "km_contacts",
     "km_solver_stats", "km_site_poses", "km_n_arm", "km_reset_host", "km_step_host",
+    "km_render", "km_render_host", "km_render_record_floats", "km_get_render_records",
 ]
 
 
@@ -70,6 +71,10 @@ def load() -> C.CDLL:
     L.km_n_arm.argtypes = [vp]
     L.km_reset_host.argtypes = [vp, vp, vp, vp]
     L.km_step_host.argtypes = [vp, vp, vp, vp, vp, ip]
+    L.km_render.argtypes = [vp, vp, vp, vp, vp]
+    L.km_render_host.argtypes = [vp, vp, vp, vp]
+    L.km_render_record_floats.argtypes = [vp]
+    L.km_get_render_records.argtypes = [vp, vp, vp]
     _LIB = L
     return L
 

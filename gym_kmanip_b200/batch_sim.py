@@ -171,6 +171,39 @@ class BatchSim:
         _lib.check(self.L.km_site_poses(self.h, pos.data_ptr(), mat.data_ptr(), self._stream()))
         return pos, mat
 
+    # ------------------------------------------------------------------ camera observations (Vision ids)
+    def render(self, cam, out=None):
+        """Image of every env's stored state from camera `cam` (a constants.Cam or its name): uint8 CUDA tensor [n, h, w, 3]."""
+        from . import render as R
+        t = self.torch
+        cam = K.CAMERAS[cam] if isinstance(cam, str) else cam
+        key = (cam.name, cam.w, cam.h)
+        if not hasattr(self, "_cams"):
+            self._cams, self._visual = {}, R.visual_struct(self.flat)
+        if key not in self._cams:
+            self._cams[key] = R.camera_struct(self.flat, cam.name, cam.w, cam.h)
+        if out is None:
+            out = t.empty(self.n, cam.h, cam.w, 3, dtype=t.uint8, device=self.device)
+        assert out.is_cuda and out.dtype == t.uint8 and out.is_contiguous() and out.numel() == self.n * cam.h * cam.w * 3
+        _lib.check(self.L.km_render(self.h, C.byref(self._cams[key]), C.byref(self._visual), out.data_ptr(), self._stream()))
+        return out
+
+    def render_host(self, cam, out: np.ndarray):
+        """km_render_host: the same with a HOST image buffer [n, h, w, 3] uint8 (copy inside)."""
+        from . import render as R
+        cam = K.CAMERAS[cam] if isinstance(cam, str) else cam
+        _lib.check(self.L.km_render_host(self.h, C.byref(R.camera_struct(self.flat, cam.name, cam.w, cam.h)),
+                                         C.byref(R.visual_struct(self.flat)), out.ctypes.data))
+        return out
+
+    def render_records(self):
+        """The per-env render records of the last render() (float32 [n, rec_floats]); for tests of the pixel stage."""
+        t = self.torch
+        nf = int(self.L.km_render_record_floats(self.h))
+        out = t.empty(self.n, nf, dtype=t.float32, device=self.device)
+        _lib.check(self.L.km_get_render_records(self.h, out.data_ptr(), self._stream()))
+        return out
+
     def solver_stats(self):
         t = self.torch
         it = t.empty(self.n, dtype=t.int32, device=self.device)

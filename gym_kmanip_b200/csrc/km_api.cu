@@ -1,9 +1,11 @@
 // km_api.cu -- the C-ABI of include/kmanip_b200.h: handle management, buffers, launches.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
+#define KM_RENDER_PIXELS_IMPL
 #include "km_launch.cuh"
 
 namespace km {
@@ -32,6 +34,11 @@ struct km_sim {
   float* d_act;
   void *d_obs, *d_reward, *d_xyz;
   unsigned char *d_trunc, *d_mask;
+  // camera observations: per-env render records, staging image for km_render_host
+  float* d_recs;
+  unsigned char* d_rgb;
+  size_t rgb_bytes;
+  double tab_z;
   long long launches;
 };
 
@@ -211,6 +218,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   std::vector<unsigned char> host_model(h->vt.model_bytes);
   std::string err;
   if (h->vt.fill(model, task, host_model.data(), err) != 0) { delete h; return fail(KM_ERR_MODEL, err); }
+  h->tab_z = h->vt.table_z(host_model.data());
   DeviceGuard guard(device);
   if (!guard.ok) { delete h; return fail(KM_ERR_CUDA, "km_create: cudaSetDevice failed"); }
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -259,7 +267,7 @@ void km_destroy(km_handle h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   void* ptrs[] = {h->d_model, h->d_state, h->d_step, h->d_episode, h->d_niter, h->d_ls, h->d_act, h->d_obs, h->d_reward,
-                  h->d_xyz, h->d_trunc, h->d_mask};
+                  h->d_xyz, h->d_trunc, h->d_mask, h->d_recs, h->d_rgb};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -368,6 +376,77 @@ int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream
   cudaStream_t s = (cudaStream_t)stream;
   if (niter_dev) KM_CUDA(cudaMemcpyAsync(niter_dev, h->d_niter, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
   if (ls_evals_dev) KM_CUDA(cudaMemcpyAsync(ls_evals_dev, h->d_ls, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return KM_OK;
+}
+
+int km_render(km_handle h, const km_camera* cam, const km_visual* vis, unsigned char* rgb_dev, void* stream) {
+  if (!h || !cam || !vis || !rgb_dev) return fail(KM_ERR_ARG, "km_render: null argument");
+  if (cam->width < 1 || cam->height < 1 || !(cam->fovy > 0 && cam->fovy < 180)) return fail(KM_ERR_ARG, "km_render: bad camera");
+  if (vis->nlight < 0 || vis->nlight > 4) return fail(KM_ERR_ARG, "km_render: at most 4 directional lights");
+  const int nlinks = h->vt.nv - 6;
+  if (cam->link >= nlinks || cam->target_link >= nlinks) return fail(KM_ERR_ARG, "km_render: camera link out of range");
+  DeviceGuard guard(h->device);
+  if (!h->d_recs) KM_CUDA(cudaMalloc((void**)&h->d_recs, (size_t)h->n * h->vt.render_rec_floats * sizeof(float)));
+  km::KmRenderParams P;
+  std::memset(&P, 0, sizeof(P));
+  P.W = cam->width; P.H = cam->height;
+  P.tiles_x = (P.W + km::KM_RENDER_TILE - 1) / km::KM_RENDER_TILE; P.tiles_y = (P.H + km::KM_RENDER_TILE - 1) / km::KM_RENDER_TILE;
+  P.rec_floats = h->vt.render_rec_floats; P.nlight = vis->nlight;
+  P.focal = (float)(0.5 * cam->height / std::tan(0.5 * cam->fovy * 3.14159265358979323846 / 180.0));
+  P.tab_z = (float)h->tab_z; P.link_radius = (float)vis->link_radius;
+  for (int c = 0; c < 3; c++) {
+    P.ambient[c] = (float)vis->head_ambient[c]; P.head_diffuse[c] = (float)vis->head_diffuse[c]; P.head_specular[c] = (float)vis->head_specular[c];
+    P.mat[km::KM_MAT_TABLE][c] = (float)vis->rgb_table[c]; P.mat[km::KM_MAT_CUBE][c] = (float)vis->rgb_cube[c];
+    P.mat[km::KM_MAT_LINK][c] = (float)vis->rgb_link[c]; P.mat[km::KM_MAT_PAD][c] = (float)vis->rgb_pad[c];
+    P.cam_pos[c] = (float)cam->pos[c]; P.tgt_pos[c] = (float)cam->target_pos[c];
+  }
+  for (int l = 0; l < vis->nlight; l++) {
+    const double* d = vis->light_dir[l];
+    const double nn = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (!(nn > 0)) return fail(KM_ERR_ARG, "km_render: zero light direction");
+    for (int c = 0; c < 3; c++) {
+      P.ldir[l][c] = (float)(-d[c] / nn); P.ldiffuse[l][c] = (float)vis->light_diffuse[l][c]; P.lspecular[l][c] = (float)vis->light_specular[l][c];
+      P.ambient[c] += (float)vis->light_ambient[l][c];
+    }
+  }
+  P.mat_specular = (float)vis->specular;
+  int k = 0;
+  while ((1 << (k + 1)) <= (int)(vis->shininess * 128.0 + 0.5)) k++;   // exponent rounded down to a power of two (0.5 -> 64)
+  P.shin_squarings = k;
+  P.cam_link = cam->link; P.tgt_link = cam->target_link;
+  KmArgs a = base_args(h, stream);
+  KM_CUDA(h->vt.render_setup(a, P, h->d_recs));
+  const dim3 grid(P.tiles_x * P.tiles_y, h->n);
+  if (h->n > 65535) return fail(KM_ERR_ARG, "km_render: at most 65535 envs per handle");
+  km::k_render_pixels<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d_recs, rgb_dev, P);
+  KM_CUDA(cudaGetLastError());
+  h->launches += 2;
+  return KM_OK;
+}
+
+int km_render_host(km_handle h, const km_camera* cam, const km_visual* vis, unsigned char* rgb_host) {
+  if (!h || !cam || !rgb_host) return fail(KM_ERR_ARG, "km_render_host: null argument");
+  DeviceGuard guard(h->device);
+  const size_t bytes = (size_t)h->n * cam->width * cam->height * 3;
+  if (bytes > h->rgb_bytes) {
+    if (h->d_rgb) cudaFree(h->d_rgb);
+    h->d_rgb = nullptr; h->rgb_bytes = 0;
+    KM_CUDA(cudaMalloc((void**)&h->d_rgb, bytes));
+    h->rgb_bytes = bytes;
+  }
+  int rc = km_render(h, cam, vis, h->d_rgb, nullptr);
+  if (rc != KM_OK) return rc;
+  KM_CUDA(cudaMemcpyAsync(rgb_host, h->d_rgb, bytes, cudaMemcpyDeviceToHost, 0));
+  KM_CUDA(cudaStreamSynchronize(0));
+  return KM_OK;
+}
+
+int km_render_record_floats(km_handle h) { return h ? h->vt.render_rec_floats : 0; }
+int km_get_render_records(km_handle h, float* recs_dev, void* stream) {
+  if (!h || !recs_dev) return fail(KM_ERR_ARG, "km_get_render_records: null argument");
+  if (!h->d_recs) return fail(KM_ERR_ARG, "km_get_render_records: km_render has not run on this handle");
+  DeviceGuard guard(h->device);
+  KM_CUDA(cudaMemcpyAsync(recs_dev, h->d_recs, (size_t)h->n * h->vt.render_rec_floats * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return KM_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <string>
 #include "km_fill.h"
+#include "km_render.cuh"
 
 namespace km {
 
@@ -48,6 +49,10 @@ struct KmVtable {
   cudaError_t (*contacts)(const KmArgs&);
   // opt in to the dynamic shared memory of (G, epb); returns resident CTAs per SM through *ctas_per_sm
   cudaError_t (*prepare)(int G, int epb, int* ctas_per_sm);
+  // camera observations: one record of floats per env (camera frame + primitive list) from the stored state
+  int render_rec_floats;
+  double (*table_z)(const void* host_model);
+  cudaError_t (*render_setup)(const KmArgs&, const KmRenderParams&, float* recs);
 };
 
 #if defined(__CUDACC__)
@@ -247,6 +252,22 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
   }
 }
 
+// Camera observations, stage 1: position stage on the stored state -> render record (km_render.cuh).  Not hot (the pixel
+// kernel is): one env per warp, four per CTA.
+template <class S, typename T, int G> __global__ void __launch_bounds__(max_threads<S, T>()) k_render_setup(KmArgs a, KmRenderParams P, float* recs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const Model<S, T>& m = stage_model<S, T>(smem, a.model);
+  const Grp<G> g = make_group<G>();
+  const int slot = threadIdx.x / G;
+  Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
+  for (long env = (long)blockIdx.x * a.epb + slot; env < a.n; env += (long)gridDim.x * a.epb) {
+    load_state<S, T, G>(e, a, env, g);
+    kinematics<S, T, G>(e, m, g);
+    render_record<S, T, G>(e, m, g, P, recs + env * render_rec_floats<S>());
+    g.sync();
+  }
+}
+
 template <class S, typename T> struct Launch {
   typedef Dim<S> D;
   template <int G> static cudaError_t run(int which, const KmArgs& a) {
@@ -280,6 +301,16 @@ template <class S, typename T> struct Launch {
   static cudaError_t step(const KmArgs& a) { return dispatch(0, a); }
   static cudaError_t reset(const KmArgs& a) { return dispatch(1, a); }
   static cudaError_t contacts(const KmArgs& a) { return dispatch(2, a); }
+  static double table_z(const void* host_model) { return (double)((const Model<S, T>*)host_model)->tab_z; }
+  static cudaError_t render_setup(const KmArgs& a, const KmRenderParams& P, float* recs) {
+    cudaError_t err = cudaFuncSetAttribute(k_render_setup<S, T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<S, T>(4));
+    if (err != cudaSuccess) return err;
+    const int grid = (a.n + 3) / 4 < 148 * 8 ? (a.n + 3) / 4 : 148 * 8;
+    KmArgs b = a;
+    b.epb = 4;
+    k_render_setup<S, T, 32><<<dim3(grid), dim3(128), smem_bytes<S, T>(4), a.stream>>>(b, P, recs);
+    return cudaGetLastError();
+  }
   template <int G> static cudaError_t prep(int epb, int* ctas) {
     // the attribute is per function, not per handle: always opt in to the device maximum so that handles with
     // different envs-per-CTA can coexist in one process
@@ -323,6 +354,7 @@ template <class S, typename T> struct Launch {
     v.model_bytes = sizeof(Model<S, T>); v.env_bytes = env_smem<S, T>(); v.scalar_bytes = sizeof(T);
     v.nq = D::NQ; v.nv = D::NV; v.nu = D::NU; v.nmocap = D::NMOCAP; v.obs_dim = D::OBS;
     v.state_dim = D::STATE; v.maxcon = D::MAXCON; v.nlanes_min = D::NV <= 16 ? 16 : 32; v.max_threads = max_threads<S, T>(); v.tpe_max_envs = Tpe<S, T>::max_envs(); v.tpe_env_bytes = Tpe<S, T>::stride;
+    v.render_rec_floats = render_rec_floats<S>(); v.render_setup = &render_setup; v.table_z = &table_z;
     v.fill = &fill; v.step = &step; v.reset = &reset; v.contacts = &contacts; v.prepare = &prepare;
     return v;
   }

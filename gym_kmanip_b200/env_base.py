@@ -6,7 +6,8 @@ observation / action spaces (float64 observations in [-1, 1], float32 actions in
 The backend is selected through the same seam (``self.env = new(self)``), bound to the CUDA backend of
 env_sim.py.  ``make(id)`` applies the 64-step TimeLimit that ``gym.make`` adds from the registration
 (reference __init__.py:28,247).  ``log_h5py=True`` writes per-episode files in the reference's layout (log_episode.py);
-the rerun logger, the real-robot backend and camera observations are out of scope and raise NotImplementedError.
+camera observations (the Vision ids, ``render()``) come from the ray-casting kernels of csrc/km_render.cuh; the rerun logger
+and the real-robot backend are out of scope and raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -36,8 +37,6 @@ class KManipEnv(GymEnv):
             raise NotImplementedError("the rerun visualisation logger is out of scope (SURVEY.md 2.1 #8)")
         if not sim:
             raise NotImplementedError("the real-robot backend is out of scope (SURVEY.md 2.1 #6)")
-        if any("camera" in o for o in obs_list):
-            raise NotImplementedError("camera observations are outside the accelerated hot path (SURVEY.md 8f rank 4)")
         self.render_mode = render_mode
         self.seed = seed
         self.step_idx = 0
@@ -49,7 +48,7 @@ class KManipEnv(GymEnv):
         assert len(q_keys) == self.q_len, "q parameters do not match"
         self.q_id_r_mask, self.q_id_l_mask = q_id_r_mask, q_id_l_mask
         self.ctrl_id_r_grip, self.ctrl_id_l_grip = ctrl_id_r_grip, ctrl_id_l_grip
-        self.cameras: list = []
+        self.cameras: list = [K.CAMERAS[o.split("/")[-1]] for o in obs_list if "camera" in o]   # env_base.py:75-80
         self.log_rerun, self.log_h5py = False, bool(log_h5py)
         self._log = None
         if self.log_h5py:   # per-episode files in the reference's layout (env_base.py:82-95, log_h5py.py)
@@ -65,6 +64,8 @@ class KManipEnv(GymEnv):
         for key, shape in (("q_pos", (self.q_len,)), ("q_vel", (self.q_len,)), ("cube_pos", (3,)), ("cube_orn", (4,))):
             if key in obs_list:
                 od[key] = Box(low=-1, high=1, shape=shape, dtype=K.OBS_DTYPE)
+        for cam in self.cameras:            # env_base.py:140-147
+            od[cam.log_name] = Box(low=cam.low, high=cam.high, shape=(cam.h, cam.w, 3), dtype=cam.dtype)
         self.observation_space = DictSpace(od)
         # action space (env_base.py:149-190)
         self.act_list = act_list

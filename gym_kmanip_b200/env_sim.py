@@ -126,10 +126,15 @@ class KManipEnvSim:
         for k in self.gym_env.obs_list:
             if k in self._obs_layout:
                 obs[k] = self._h_obs[0, self._obs_layout[k]].astype(K.OBS_DTYPE)
+        for cam in self.gym_env.cameras:      # env_sim.py:140-145
+            obs[cam.log_name] = self.k_render(cam)
         return obs
 
     def k_render(self, cam):
-        raise NotImplementedError("camera rendering is outside the accelerated hot path (SURVEY.md 8f rank 4)")
+        """reference env_sim.py:187-188: uint8 [h, w, 3] image of camera `cam` (a constants.Cam)."""
+        img = np.empty((1, cam.h, cam.w, 3), dtype=np.uint8)
+        self.sim.render_host(cam, img)
+        return img[0]
 
     def k_reset(self, cube_xyz: Optional[np.ndarray] = None):
         xyz = None if cube_xyz is None else np.ascontiguousarray(cube_xyz, dtype=self._h_obs.dtype).reshape(1, 3)

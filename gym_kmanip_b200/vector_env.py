@@ -23,8 +23,6 @@ class KManipVectorEnv:
     def __init__(self, env_id: str, num_envs: int, device: int = 0, dtype: str = "float32", seed: int = 0, env0: int = 0,
                  max_episode_steps: int = K.MAX_EPISODE_STEPS, log_dir: Optional[str] = None, log_env_ids=None, **sim_kwargs):
         kw = K.ENV_REGISTRY[env_id]
-        if any("camera" in o for o in kw["obs_list"]):
-            raise NotImplementedError("camera observations are outside the accelerated hot path (SURVEY.md 8f rank 4)")
         self.env_id, self.num_envs = env_id, int(num_envs)
         self.sim = BatchSim(env_id, num_envs, device=device, dtype=dtype, seed=seed, env0=env0,
                             max_episode_steps=max_episode_steps, **sim_kwargs)
@@ -34,8 +32,14 @@ class KManipVectorEnv:
         n_l = len(kw["q_id_l_mask"]) if kw.get("q_id_l_mask") is not None else 0
         self.action_layout = action_layout(self.act_list, n_r, n_l)
         self.obs_layout = {k: v for k, v in obs_layout(self.sim.q_len).items() if k in self.obs_list}
-        self.single_observation_space = DictSpace(OrderedDict(
-            (k, Box(-1, 1, (sl.stop - sl.start,), K.OBS_DTYPE)) for k, sl in self.obs_layout.items()))
+        # camera observations of the Vision ids (reference env_base.py:140-147): one uint8 image batch per camera, rendered
+        # from the post-step state by the ray-casting kernels (csrc/km_render.cuh)
+        self.cameras = [K.CAMERAS[o.split("/")[-1]] for o in self.obs_list if "camera" in o]
+        spaces_ = [(k, Box(-1, 1, (sl.stop - sl.start,), K.OBS_DTYPE)) for k, sl in self.obs_layout.items()]
+        spaces_ += [(c.log_name, Box(c.low, c.high, (c.h, c.w, 3), c.dtype)) for c in self.cameras]
+        self.single_observation_space = DictSpace(OrderedDict(spaces_))
+        self._images = {c.log_name: self.sim.torch.empty(self.num_envs, c.h, c.w, 3, dtype=self.sim.torch.uint8, device=self.sim.device)
+                        for c in self.cameras}
         self.single_action_space = DictSpace(OrderedDict(
             (k, Box(-1, 1, (sl.stop - sl.start,), K.ACT_DTYPE)) for k, sl in self.action_layout.items()))
         t = self.sim.torch
@@ -49,12 +53,16 @@ class KManipVectorEnv:
             from .log_episode import BatchEpisodeLog
             ids = [0] if log_env_ids is None else list(log_env_ids)
             self.log = BatchEpisodeLog(log_dir, ids, self.sim.q_len, len(self.action_layout), self.action_layout["grip_r"].start,
-                                       t, self.device, env0=env0, max_steps=max_episode_steps,
+                                       t, self.device, env0=env0,
                                        info={"env_id": env_id, "obs_list": self.obs_list, "act_list": self.act_list})
 
     # -------------------------------------------------------------------------------- helpers
-    def _obs_dict(self, flat) -> "OrderedDict[str, object]":
-        return OrderedDict((k, flat[:, sl]) for k, sl in self.obs_layout.items())
+    def _obs_dict(self, flat, images: bool = True) -> "OrderedDict[str, object]":
+        obs = OrderedDict((k, flat[:, sl]) for k, sl in self.obs_layout.items())
+        if images:
+            for c in self.cameras:          # images of the stored (post-step, post-autoreset) state; buffers are reused
+                obs[c.log_name] = self.sim.render(c, out=self._images[c.log_name])
+        return obs
 
     def flatten_action(self, action):
         """Dict of [n, k] tensors (reference keys) -> the flat [n, act_dim] float32 record; flat tensors pass through."""
@@ -91,7 +99,7 @@ class KManipVectorEnv:
         done = trunc.bool()
         self.episode_return += rew.double()
         info: Dict[str, object] = {
-            "is_success": success, "final_obs": self._obs_dict(self.sim.final_obs),
+            "is_success": success, "final_obs": self._obs_dict(self.sim.final_obs, images=False),
             "final_return": t.where(done, self.episode_return, t.zeros_like(self.episode_return)),
             "con_flags": self.sim.con_flags, "ncon": self.sim.ncon,
         }

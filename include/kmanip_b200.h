@@ -151,6 +151,39 @@ int km_contacts(km_handle h, int* ncon_dev, int* con_geoms_dev, void* stream);
 int km_site_poses(km_handle h, void* xpos_dev, void* xmat_dev, void* stream);
 int km_n_arm(km_handle h);
 
+/* Camera observations of the Vision ids  <- gym_kmanip/env_sim.py:140-145 (get_observation: physics.render(height=cam.h,
+   width=cam.w, camera_id=cam.name) for every camera of obs_list) and env_sim.py:187-188 (k_render(cam)); camera sizes are
+   the Cam table of __init__.py:157-161.  Renders the stored state of every env: rgb_dev [n][height][width][3] uint8,
+   row 0 on top.  What is drawn is the completed model's primitives (table plane, cube, finger pads, one capsule per
+   moving link) under MuJoCo's camera / fixed-function lighting conventions; see csrc/km_render.cuh.
+   km_camera: an MJCF <camera mode="targetbody"> (reference _env_solo_arm.xml:14-15, arm_r_body.xml:68) after the host
+   folded static bodies away: `link` is the joint index of the moving body the camera rides on (-1: fixed in the world),
+   `pos` its position in that body's frame (or the world); the tracked body's origin likewise. */
+typedef struct km_camera {
+  int width, height;
+  double fovy;               /* vertical field of view, degrees */
+  int link;
+  double pos[3];
+  int target_link;
+  double target_pos[3];
+} km_camera;
+/* Lights and colours: <visual><headlight>, the directional <light>s and geom rgba of scene.xml:5-20, and the appearance
+   the completion spec gives the link proxies.  light_dir is the direction the light travels (MJCF `dir`). */
+typedef struct km_visual {
+  int nlight;                /* directional lights, at most 4 */
+  double light_dir[4][3], light_diffuse[4][3], light_specular[4][3], light_ambient[4][3];
+  double head_ambient[3], head_diffuse[3], head_specular[3];
+  double rgb_table[3], rgb_cube[3], rgb_link[3], rgb_pad[3];
+  double specular, shininess; /* material defaults of MuJoCo: 0.5, 0.5 (exponent shininess * 128) */
+  double link_radius;
+} km_visual;
+int km_render(km_handle h, const km_camera* cam, const km_visual* vis, unsigned char* rgb_dev, void* stream);
+int km_render_host(km_handle h, const km_camera* cam, const km_visual* vis, unsigned char* rgb_host);
+/* Copy of the per-env render records of the last km_render ([n][km_render_record_floats] float32: camera origin and
+   axes, then 16 floats per primitive) -- exposed so that tests can check the pixel stage against the oracle exactly. */
+int km_render_record_floats(km_handle h);
+int km_get_render_records(km_handle h, float* recs_dev, void* stream);
+
 /* Diagnostics of the most recent step's last sub-step: [n] Newton iterations, [n] line-search evaluations (cumulative). */
 int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream);
 

@@ -14,6 +14,10 @@ What pins what (the reference's own tests hold no numeric vectors, SURVEY.md sec
   traj_<env>.npz        teacher-forcing records of the oracle (state before, action, outputs, state after): pins the
                         oracle against accidental change and is what the CUDA path is compared with on the GPU box
                         without needing to run the oracle there.
+  render_<env>.npz      camera observations of the Vision ids: four mid-episode states of the trajectory fixture, the
+                        oracle's render records (oracle/render_oracle.py: camera frame + primitive list from the C++
+                        oracle's body frames) and its ray-cast images (head camera at 160 x 120, gripper cameras at their
+                        own 60 x 40); pins the numpy restatement and is what km_render is compared with on the GPU box.
 """
 import json
 import os
@@ -110,12 +114,42 @@ def trajectories():
         np.savez_compressed(os.path.join(HERE, f"traj_{env_id}.npz"), **rec)
 
 
+RENDER_ENVS = {"KManipSoloArm": ["head", "grip_r"], "KManipDualArm": ["head", "grip_l", "grip_r"], "KManipTorso": ["head", "grip_l", "grip_r"]}
+RENDER_SIZE = {"head": (160, 120), "grip_r": (60, 40), "grip_l": (60, 40)}
+
+
+def render_fixtures():
+    from oracle import render_oracle as ro
+    for env_id, cams in RENDER_ENVS.items():
+        traj = np.load(os.path.join(HERE, f"traj_{env_id}.npz"))
+        states = traj["s40_after"][:4]
+        o = om.Oracle(env_id)
+        nq, nv, nu = o.nq, o.nv, o.nu
+        rec = {"state": states}
+        frames = []
+        for st in states:
+            o.set_state(st[:nq], st[nq:nq + nv], st[nq + nv:nq + nv + nu])
+            o.mj_forward(disable_actuation=True)
+            frames.append((o.field("xpos").reshape(-1, 3), o.field("xquat").reshape(-1, 4)))
+        for cam in cams:
+            w, h = RENDER_SIZE[cam]
+            P = ro.params(o.flat, cam, w, h)
+            recs = np.stack([ro.scene_record(o.flat, xp, xq, cam) for xp, xq in frames])
+            rec[f"rec_{cam}"] = recs
+            rec[f"img_{cam}"] = np.stack([ro.render_record(r, P) for r in recs])
+        np.savez_compressed(os.path.join(HERE, f"render_{env_id}.npz"), **rec)
+
+
 def main():
     om.build()
+    if "--render-only" in sys.argv:
+        render_fixtures()
+        return
     json.dump(scipy_rotation(), open(os.path.join(HERE, "scipy_rotation.json"), "w"))
     json.dump(ik_trf(), open(os.path.join(HERE, "ik_trf.json"), "w"))
     json.dump(fk_home(), open(os.path.join(HERE, "fk_home.json"), "w"), indent=1)
     trajectories()
+    render_fixtures()
     print("golden fixtures written to", HERE)
 
 

@@ -183,6 +183,7 @@ def test_single_env_episode_logging(tmp_path, monkeypatch):
 def test_vector_env_episode_logging_from_device_ring_buffers(tmp_path):
     """KManipVectorEnv(log_dir=...): logged envs' rows stay on the device until truncation, then one file per episode."""
     import torch
+    from gym_kmanip_b200.vector_env import KManipVectorEnv
     env = KManipVectorEnv("KManipSoloArmQPos", 64, seed=3, max_episode_steps=4, log_dir=str(tmp_path), log_env_ids=[0, 63])
     obs, _ = env.reset()
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -191,7 +192,7 @@ def test_vector_env_episode_logging_from_device_ring_buffers(tmp_path):
         act = env.sample_actions(g)
         obs, rew, term, trunc, info = env.step(act)
         src = torch.where(trunc.bool()[:, None], env.sim.final_obs, env.sim.obs)
-        rows.append((act[63, 7].item(), src[63, :10].float().cpu().numpy()))
+        rows.append((act[63, env.action_layout["grip_r"].start].item(), src[63, :10].float().cpu().numpy()))
     files = sorted(os.listdir(tmp_path))
     assert [f.split(".")[0] for f in files] == ["env000000_episode_1", "env000000_episode_2", "env000063_episode_1", "env000063_episode_2"]
     if files[-1].endswith(".npz"):

@@ -77,10 +77,10 @@ def test_shard_ranges_partition_the_job():
         sharding.shard_range(8, 2, 2)
 
 
-def test_vision_ids_and_loggers_are_declared_out_of_scope():
+def test_rerun_logger_and_real_robot_are_declared_out_of_scope():
     from gym_kmanip_b200.env_base import KManipEnv
     with pytest.raises(NotImplementedError):
-        KManipEnv(**K.ENV_REGISTRY["KManipSoloArmVision"])
+        KManipEnv(**dict(K.ENV_REGISTRY["KManipSoloArm"], sim=False))
     with pytest.raises(NotImplementedError):
         KManipEnv(**dict(K.ENV_REGISTRY["KManipSoloArm"], log_rerun=True))
     with pytest.raises(KeyError):

@@ -15,3 +15,14 @@ for env in ("KManipSoloArm", "KManipDualArm"):
         torch.cuda.synchronize()
         s.close()
         print(env, lanes, "ok", flush=True)
+# camera observations: setup + pixel kernels, aligned (640 x 480) and unaligned (60 x 40) store paths, partial tiles
+for env, cams in (("KManipSoloArmVision", ("head", "grip_r")), ("KManipTorsoVision", ("top", "grip_l"))):
+    s = BatchSim(env, 3, dtype="float32", seed=1)
+    s.reset()
+    for c in cams:
+        img = s.render(c)
+        assert img.any()
+    s.render_records()
+    torch.cuda.synchronize()
+    s.close()
+    print(env, "render ok", flush=True)
