@@ -220,8 +220,10 @@ __global__ void __launch_bounds__(256) k_render_pixels(const float* __restrict__
   __shared__ float rec[KM_REC_HDR + KM_PRIM_FLOATS * KM_RENDER_MAXPRIM];
   __shared__ unsigned s_mask;
   __shared__ __align__(16) unsigned char tile[KM_RENDER_TILE * KM_RENDER_TILE * 3];
-  const int tid = threadIdx.x, env = blockIdx.y;
-  const int tx0 = (blockIdx.x % P.tiles_x) * KM_RENDER_TILE, ty0 = (blockIdx.x / P.tiles_x) * KM_RENDER_TILE;
+  // blockIdx.x = env * tiles + tile (grid.x reaches 2^31 - 1: no limit on the batch worth naming)
+  const int ntiles = P.tiles_x * P.tiles_y;
+  const int tid = threadIdx.x, env = blockIdx.x / ntiles, tl = blockIdx.x % ntiles;
+  const int tx0 = (tl % P.tiles_x) * KM_RENDER_TILE, ty0 = (tl / P.tiles_x) * KM_RENDER_TILE;
   const float* src = recs + (size_t)env * P.rec_floats;
   for (int i = tid; i < P.rec_floats; i += 256) rec[i] = src[i];
   __syncthreads();

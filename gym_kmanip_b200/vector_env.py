@@ -42,6 +42,12 @@ class KManipVectorEnv:
                         for c in self.cameras}
         self.single_action_space = DictSpace(OrderedDict(
             (k, Box(-1, 1, (sl.stop - sl.start,), K.ACT_DTYPE)) for k, sl in self.action_layout.items()))
+        # batched spaces as gymnasium.vector.VectorEnv exposes them (leading num_envs axis)
+        self.observation_space = DictSpace(OrderedDict(
+            (k, Box(float(sp.low.min()), float(sp.high.max()), (self.num_envs,) + tuple(sp.shape), sp.dtype))
+            for k, sp in self.single_observation_space.spaces.items()))
+        self.action_space = DictSpace(OrderedDict(
+            (k, Box(-1, 1, (self.num_envs,) + tuple(sp.shape), sp.dtype)) for k, sp in self.single_action_space.spaces.items()))
         t = self.sim.torch
         self._act = t.zeros(self.num_envs, self.sim.act_dim, dtype=t.float32, device=self.device)
         self.episode_return = t.zeros(self.num_envs, dtype=t.float64, device=self.device)

@@ -41,7 +41,7 @@ def test_committed_flat_models_are_current(scene):
     a, b = json.loads(json.dumps(flat)), json.loads(json.dumps(committed))
     assert a.keys() == b.keys()
     for key in a:
-        if isinstance(a[key], (list, float)) and key not in ("body_name", "jnt_name", "site_name", "geom_name"):
+        if isinstance(a[key], (list, float)) and key not in ("body_name", "jnt_name", "site_name", "geom_name", "cam_name"):
             assert np.allclose(np.array(a[key], dtype=float), np.array(b[key], dtype=float), rtol=1e-13, atol=1e-15), key
         else:
             assert a[key] == b[key], key

@@ -78,6 +78,9 @@ def test_vector_env_autoreset_and_totals():
     obs, _ = env.reset()
     assert list(obs) == ["q_pos", "q_vel", "cube_pos", "cube_orn"] and obs["q_pos"].shape == (n, 20) and obs["cube_orn"].shape == (n, 4)
     first = {kk: v.clone() for kk, v in obs.items()}
+    # batched spaces, as gymnasium.vector.VectorEnv exposes them
+    assert env.observation_space.spaces["q_pos"].shape == (n, 20) and env.action_space.spaces["eer_pos"].shape == (n, 3)
+    assert env.single_action_space.spaces["grip_l"].shape == (1,) and env.observation_space.contains({kk: v.cpu().numpy() for kk, v in obs.items()})
     gen = torch.Generator(device="cuda").manual_seed(0)
     for t in range(k.MAX_EPISODE_STEPS + 2):
         flat = env.sample_actions(gen)
