@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,7 +27,7 @@ struct km_sim {
   KmVtable vt;
   int scene, dtype, n, device, act_dim, n_arm;
   unsigned long long seed, env0;
-  int G, epb, grid, ctas_per_sm, num_sms, lpw;
+  int G, epb, grid, ctas_per_sm, num_sms, lpw, tpl_ctas;
   void* d_model;
   void* d_state;
   int *d_step, *d_episode, *d_niter, *d_ls;
@@ -62,17 +63,21 @@ struct DeviceGuard {
 // envs per CTA of the thread-per-env (local memory) mapping: one CTA per SM holding its share of the batch, equal
 // CTAs in as few full waves as possible (measured: 65536 solo-arm envs as 147 CTAs of 446 envs 6.6e6 env-steps/s, as
 // 256 tiles of 256 over 148 CTAs 5.4e6)
-static int tpe_local_envs(const km_sim* h) {
-  const long cap = 512, per_wave = (long)h->num_sms * cap;
+static int tpe_local_envs(const km_sim* h, int ctas) {
+  const long cap = 512 / ctas, slots = (long)h->num_sms * ctas, per_wave = slots * cap;
   const long waves = ((long)h->n + per_wave - 1) / per_wave;
-  const long per_cta = ((long)h->n + h->num_sms * waves - 1) / (h->num_sms * waves);
+  const long per_cta = ((long)h->n + slots * waves - 1) / (slots * waves);
   return (int)(per_cta > cap ? cap : per_cta);
 }
 
 static int configure(km_sim* h, int G, int epb) {
   if (G == 0) G = h->G;
   if (G == 2) {   // thread-per-env with the env record in local memory: epb = threads per CTA (32..256)
-    if (epb == 0) epb = tpe_local_envs(h);
+    // experiment knob: KM_TPL_CTAS = CTAs per SM of this mapping (default 1; more CTAs = smaller barrier domains)
+    const char* ev = std::getenv("KM_TPL_CTAS");
+    const int want = ev ? std::atoi(ev) : 1;
+    h->tpl_ctas = want >= 1 && want <= 4 ? want : 1;
+    if (epb == 0) epb = tpe_local_envs(h, h->tpl_ctas);
     // Active lanes per warp: all 32.  Dealing the envs of a CTA to more warps with fewer active lanes each was measured
     // and is far worse (4096 solo-arm envs as 14 warps x 2 lanes per SM: 6.7 ms per launch against 2.7 ms): every
     // warp executes the whole instruction stream, so issue slots, not latency, become the limit.
@@ -82,8 +87,8 @@ static int configure(km_sim* h, int G, int epb) {
     int ctas = 0;
     KM_CUDA(h->vt.prepare(2, threads, &ctas));
     if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
-    // one CTA per SM: the records of the resident envs (6.9 KB each for the solo arm) should stay in L2
-    ctas = 1;
+    // one CTA per SM by default: the records of the resident envs (6.9 KB each for the solo arm) should stay in L2
+    ctas = h->tpl_ctas;
     h->G = 2; h->epb = epb; h->ctas_per_sm = ctas;
     const long tiles = ((long)h->n + epb - 1) / epb, resident = (long)h->num_sms * ctas;
     h->grid = (int)(tiles < resident ? tiles : resident);
@@ -141,7 +146,7 @@ static KmArgs base_args(km_sim* h, void* stream) {
   std::memset(&a, 0, sizeof(a));
   a.model = h->d_model; a.state = h->d_state; a.step = h->d_step; a.episode = h->d_episode;
   a.niter = h->d_niter; a.ls = h->d_ls;
-  a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid; a.lpw = h->lpw > 0 ? h->lpw : 32;
+  a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid; a.lpw = h->lpw > 0 ? h->lpw : 32; a.tpl_small_regs = h->tpl_ctas > 1;
   a.stream = (cudaStream_t)stream;
   return a;
 }

@@ -37,6 +37,7 @@ struct KmArgs {
   unsigned long long seed, env0;
   int G, epb, grid;
   int lpw;   // thread-per-env (local) mapping: active lanes per warp (envs of a CTA are spread over its warps)
+  int tpl_small_regs;   // thread-per-env (local): use the 128-register instantiation even for CTAs of <= 256 threads (several CTAs per SM)
   cudaStream_t stream;
 };
 
@@ -285,7 +286,7 @@ template <class S, typename T> struct Launch {
     }
     if (a.G == 2 && which == 0) {   // thread per env, record in local memory
       const int threads = (a.epb + a.lpw - 1) / a.lpw * 32;   // warps needed to hold epb envs at lpw active lanes each
-      if (threads <= 256) k_env_step_tpe<S, T, true, 256><<<dim3(a.grid), dim3(threads), model_smem<S, T>(), a.stream>>>(a);
+      if (threads <= 256 && !a.tpl_small_regs) k_env_step_tpe<S, T, true, 256><<<dim3(a.grid), dim3(threads), model_smem<S, T>(), a.stream>>>(a);
       else k_env_step_tpe<S, T, true, 512><<<dim3(a.grid), dim3(threads), model_smem<S, T>(), a.stream>>>(a);
       return cudaGetLastError();
     }
