@@ -25,7 +25,7 @@ static thread_local std::string g_err;
 
 struct km_sim {
   KmVtable vt;
-  int scene, dtype, n, device, act_dim, n_arm;
+  int scene, dtype, n, device, act_dim, n_arm, ik_mode;
   unsigned long long seed, env0;
   int G, epb, grid, ctas_per_sm, num_sms, lpw, tpl_ctas;
   void* d_model;
@@ -72,6 +72,8 @@ static int tpe_local_envs(const km_sim* h, int ctas) {
 
 static int configure(km_sim* h, int G, int epb) {
   if (G == 0) G = h->G;
+  if (h->ik_mode == 1 && (G == 1 || G == 2))
+    return fail(KM_ERR_ARG, "ik_mode = 1 (exact-parity TRF IK) runs in the lane-group mapping only (lanes_per_env 16 / 32)");
   if (G == 2) {   // thread-per-env with the env record in local memory: epb = threads per CTA (32..256)
     // experiment knob: KM_TPL_CTAS = CTAs per SM of this mapping (default 1; more CTAs = smaller barrier domains)
     const char* ev = std::getenv("KM_TPL_CTAS");
@@ -219,7 +221,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
     case 5: h->vt = km::vtable_torso_f64(); break;
     default: delete h; return fail(KM_ERR_ARG, "km_create: unknown scene");
   }
-  h->scene = scene; h->dtype = dtype; h->n = n_envs; h->device = device; h->seed = seed; h->env0 = env0; h->act_dim = task->act_dim; h->n_arm = task->n_arm;
+  h->scene = scene; h->dtype = dtype; h->n = n_envs; h->device = device; h->seed = seed; h->env0 = env0; h->act_dim = task->act_dim; h->n_arm = task->n_arm; h->ik_mode = task->ik_mode;
   std::vector<unsigned char> host_model(h->vt.model_bytes);
   std::string err;
   if (h->vt.fill(model, task, host_model.data(), err) != 0) { delete h; return fail(KM_ERR_MODEL, err); }
@@ -258,7 +260,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   const int per_sm = (n_envs + h->num_sms - 1) / h->num_sms;
   int rc;
   const int tpe_from = h->vt.nv > 16 ? 48 : 96;   // envs per SM from which the thread-per-env kernel wins (dual-arm / torso: 48)
-  if (per_sm >= tpe_from) rc = configure(h, 2, 0);
+  if (per_sm >= tpe_from && h->ik_mode != 1) rc = configure(h, 2, 0);   // the exact-parity IK mode lives in the lane-group kernels
   else {
     h->G = 32;
     rc = configure(h, 32, 0);
@@ -418,6 +420,7 @@ int km_render(km_handle h, const km_camera* cam, const km_visual* vis, unsigned 
   int k = 0;
   while ((1 << (k + 1)) <= (int)(vis->shininess * 128.0 + 0.5)) k++;   // exponent rounded down to a power of two (0.5 -> 64)
   P.shin_squarings = k;
+  P.spec_cut = (float)std::exp2(-20.0 / (double)(1 << k));
   P.cam_link = cam->link; P.tgt_link = cam->target_link;
   KmArgs a = base_args(h, stream);
   KM_CUDA(h->vt.render_setup(a, P, h->d_recs));

@@ -6,7 +6,7 @@
 // (assets/completion_spec.json): the table plane, the cube box, the finger-pad spheres and one capsule per moving link
 // (parent link origin -> link origin; a link-mounted camera does not see the proxies that end at its own link).  Shading follows MuJoCo's fixed-function conventions (Blinn-Phong per light:
 // headlight at the camera + the directional lights of scene.xml:10-12, material = geom rgba, specular 0.5, shininess
-// 0.5 * 128), evaluated per pixel; no shadows, fog or reflections.  Camera frames are MuJoCo's: the camera looks along
+// 0.5 * 128; highlight terms below 1e-6 are dropped), evaluated per pixel; no shadows, fog or reflections.  Camera frames are MuJoCo's: the camera looks along
 // -z with +y up, `mode="targetbody"` turns z away from the target body and x orthogonal to z and world up
 // (mj_camlight), vertical field of view `fovy`, pixel centres at half-integers, row 0 on top.
 //
@@ -33,6 +33,7 @@ struct KmRenderParams {
   float ldir[4][3], ldiffuse[4][3], lspecular[4][3];   // ldir: unit vector TOWARDS the light
   float mat[4][3], mat_specular;
   int shin_squarings;                                  // shininess exponent 2^k
+  float spec_cut;                                      // cosines below 2^(-20 / exponent) have no highlight: x^exponent < 1e-6 is dropped
   // camera: position in its link's frame (link < 0: world), tracked point likewise
   int cam_link, tgt_link;
   float cam_pos[3], tgt_pos[3];
@@ -199,8 +200,11 @@ __device__ __forceinline__ float shin_pow(float x, int k) {
 __device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, const float* V, int mat, float* rgb) {
   float dif[3] = {P.ambient[0], P.ambient[1], P.ambient[2]}, spc[3] = {0, 0, 0};
   const float nv = fmaxf(rdot(N, V), 0.0f);
-  const float s = shin_pow(nv, P.shin_squarings);
-  for (int c = 0; c < 3; c++) { dif[c] += P.head_diffuse[c] * nv; spc[c] += P.head_specular[c] * s; }
+  for (int c = 0; c < 3; c++) dif[c] += P.head_diffuse[c] * nv;
+  if (nv > P.spec_cut) {   // warp-coherent in practice: highlights are compact blobs
+    const float s = shin_pow(nv, P.shin_squarings);
+    for (int c = 0; c < 3; c++) spc[c] += P.head_specular[c] * s;
+  }
 #pragma unroll
   for (int l = 0; l < 4; l++) {   // fixed trip count: the light constants become immediate constant-bank operands
     if (l < P.nlight) {
@@ -208,8 +212,12 @@ __device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, c
       if (nl > 0.0f) {
         float Hh[3] = {P.ldir[l][0] + V[0], P.ldir[l][1] + V[1], P.ldir[l][2] + V[2]};
         rnorm(Hh);
-        const float sh = shin_pow(fmaxf(rdot(N, Hh), 0.0f), P.shin_squarings);
-        for (int c = 0; c < 3; c++) { dif[c] += P.ldiffuse[l][c] * nl; spc[c] += P.lspecular[l][c] * sh; }
+        const float nh = rdot(N, Hh);
+        for (int c = 0; c < 3; c++) dif[c] += P.ldiffuse[l][c] * nl;
+        if (nh > P.spec_cut) {
+          const float sh = shin_pow(nh, P.shin_squarings);
+          for (int c = 0; c < 3; c++) spc[c] += P.lspecular[l][c] * sh;
+        }
       }
     }
   }

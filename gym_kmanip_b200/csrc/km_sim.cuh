@@ -1027,9 +1027,20 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
     for (int i = 0; i < 7; i++) e.mocap[7 * m.arm_mocap[a] + i] = (T)b.goal[i];
   }
   g.sync();
-  if (feasible && m.ik_mode == 1) {
+  // The exact-parity mode is compiled into the lane-group kernels only (and the host build): its serial fp64 code in a
+  // thread-per-env kernel made ptxas halve the register budget of the whole kernel (255 -> 128 registers, 7x the spills
+  // in the solver: DualArm 32768 envs 2.65 -> 2.27e6 env-steps/s).  km_api.cu routes ik_mode = 1 handles to the
+  // lane-group mapping, so no mapping runs the other optimiser silently.
+#if defined(__CUDA_ARCH__)
+  constexpr bool kTrf = G > 1;
+#else
+  constexpr bool kTrf = true;
+#endif
+  bool trf = false;
+  if constexpr (kTrf) trf = feasible && m.ik_mode == 1;
+  if (trf) {
     // exact-parity mode: the reference's optimiser (scipy TRF) restated, km_ik_trf.cuh; one lane, fp64
-    if (g.lane == 0) ik_trf_serial<S, T>(e, b, m, a);
+    if constexpr (kTrf) { if (g.lane == 0) ik_trf_serial<S, T>(e, b, m, a); }
     g.sync();
   } else if (feasible) {
     const double lam = 9e-3 * (6e-3 + 2e-6), reg = 9e-3;   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)

@@ -122,7 +122,8 @@ int km_num_envs(km_handle h);
 int km_dtype(km_handle h);
 /* launch configuration.  lanes_per_env: 32 / 16 = lane group per env (at least the dof count); 1 = thread per env with the
    env records in shared memory; 2 = thread per env with the records in local memory; 0 keeps the current mapping.
-   envs_per_block: envs per CTA, 0 = choose.  km_create picks a default from the batch size. */
+   envs_per_block: envs per CTA, 0 = choose.  km_create picks a default from the batch size.
+   Handles created with km_task.ik_mode = 1 (exact-parity TRF IK) run in the lane-group mapping only: 1 / 2 are refused. */
 int km_configure(km_handle h, int lanes_per_env, int envs_per_block);
 long long km_launch_count(km_handle h);   /* kernels launched by this handle so far */
 int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* grid, int* ctas_per_sm, int* smem_bytes);

@@ -61,7 +61,7 @@ def params(flat: Dict, cam_name: str, width: int, height: int) -> Dict:
         lspecular=f32(flat["light_specular"]),
         mat=f32([flat["geom_rgba"][gi_table][:3], flat["geom_rgba"][flat["geom_name"].index("cube")][:3], vis["link_rgba"][:3],
                  flat["geom_rgba"][flat["geom_type"].index(GEOM_SPHERE)][:3]]),
-        mat_specular=np.float32(vis["specular"]), squarings=k, link_radius=np.float32(vis["link_radius"]), cam=ci)
+        mat_specular=np.float32(vis["specular"]), squarings=k, spec_cut=np.float32(2.0 ** (-20.0 / (1 << k))), link_radius=np.float32(vis["link_radius"]), cam=ci)
 
 
 def scene_record(flat: Dict, xpos: np.ndarray, xquat: np.ndarray, cam_name: str) -> np.ndarray:
@@ -210,15 +210,18 @@ def render_record(rec: np.ndarray, P: Dict) -> np.ndarray:
     s = nv.copy()
     for _ in range(P["squarings"]):
         s = s * s
+    s = np.where(nv > P["spec_cut"], s, f(0))           # highlight terms below 1e-6 are dropped (as the kernel does)
     dif = P["ambient"][None, :] + P["head_diffuse"][None, :] * nv[:, None]
     spc = P["head_specular"][None, :] * s[:, None]
     for l in range(len(P["ldir"])):
         L = P["ldir"][l]
         nl = nrm @ L
         Hh = _norm(L[None, :] + V)
-        sh = np.maximum(_dot(nrm, Hh), f(0))
+        nh = _dot(nrm, Hh)
+        sh = np.maximum(nh, f(0))
         for _ in range(P["squarings"]):
             sh = sh * sh
+        sh = np.where(nh > P["spec_cut"], sh, f(0))
         on = nl > 0
         dif = dif + np.where(on[:, None], P["ldiffuse"][l][None, :] * nl[:, None], f(0))
         spc = spc + np.where(on[:, None], P["lspecular"][l][None, :] * sh[:, None], f(0))
