@@ -391,21 +391,35 @@ template <class S, typename T, class E> struct TpeSolver {
   KM_HD void ls_eval(T qg1, T qg2, T alpha, T* d1, T* d2) {
     auto& t = e.t;
     T q1 = 0, q2 = 0;
-    sfor<0, NF>([&](auto R) {
-      constexpr int r = decltype(R)::value;
+    // Rolled on purpose (KM_TPE_LS_UNROLL = 1 restores the unrolled form): this function is two thirds of the kernel's
+    // dynamic instructions, and unrolled over the 8 friction and 10 limit rows its loop body is 36 KB of SASS, more than
+    // the 32 KB instruction cache the warps of an SM share.  Same rows in the same order: identical results.
+#ifndef KM_TPE_LS_UNROLL
+#define KM_TPE_LS_UNROLL 0
+#endif
+#if KM_TPE_LS_UNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+    for (int r = 0; r < NF; r++) {
       const T jv = t.jv_f[r], jar = t.jar_f[r], x = jar + alpha * jv, rf = m.fr_Rf[r];
       if (x <= -rf) q1 += -m.fr_loss[r] * jv;
       else if (x >= rf) q1 += m.fr_loss[r] * jv;
       else { q1 += m.fr_D[r] * jar * jv; q2 += T(0.5) * m.fr_D[r] * jv * jv; }
-    });
-    sfor<0, NVA>([&](auto Jj) {
-      constexpr int j = decltype(Jj)::value;
+    }
+#if KM_TPE_LS_UNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+    for (int j = 0; j < NVA; j++) {
       const int r = e.dof_lim[j];
       if (r >= 0) {
         const T jv = t.jv_l[j], jar = t.jar_l[j];
         if (jar + alpha * jv < T(0)) { const T Dr = e.efc_D[r]; q1 += Dr * jar * jv; q2 += T(0.5) * Dr * jv * jv; }
       }
-    });
+    }
     for (int ci = 0; ci < nc; ci++) {
       const T Dc = e.con_D[ci], a0 = t.jarb[ci][0], v0 = t.jvb[ci][0];
       for (int k = 0; k < 3; k++) {
