@@ -93,7 +93,8 @@ KM_TPL KM_FN void com_crb(KM_ARGS) {
     for (int j = i; j >= 0; j = m.parent[j]) {
       T s = 0;
       for (int k = 0; k < 6; k++) s += e.a.cdof[j][k] * buf[k];
-      e.M[i][j] = s; e.M[j][i] = s;
+      e.M[i][j] = s;
+      if constexpr (!E::TPE) e.M[j][i] = s;   // the thread-per-env solver reads the lower triangle only (km_solver_tpe.cuh)
     }
   }
   g.sync();

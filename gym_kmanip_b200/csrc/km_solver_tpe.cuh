@@ -17,6 +17,16 @@
 // block-sized and in registers.
 #pragma once
 
+// KM_TPE_K_ROLL = 1 keeps the loops over the three pyramid edge pairs of a contact rolled (smaller hot loop bodies)
+#ifndef KM_TPE_K_ROLL
+#define KM_TPE_K_ROLL 0
+#endif
+#if KM_TPE_K_ROLL
+#define KM_K_LOOP _Pragma("unroll 1")
+#else
+#define KM_K_LOOP
+#endif
+
 namespace km {
 
 KM_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -87,7 +97,9 @@ template <class S, typename T, int B0, class E> KM_HD void tpe_arm_mulM(const E&
     sfor<0, n>([&](auto I) {
       constexpr int i = decltype(I)::value;
       T s = 0;
-      sfor<0, n>([&](auto J) { constexpr int j = decltype(J)::value; s += e.M[B0 + i][B0 + j] * xv[j]; });
+      // lower triangle only: M is symmetric by construction (com_crb stores one value in both halves), so the result is
+      // identical and the upper half drops out of the solver's hot set in local memory
+      sfor<0, n>([&](auto J) { constexpr int j = decltype(J)::value; s += e.M[B0 + (i > j ? i : j)][B0 + (i > j ? j : i)] * xv[j]; });
       out[B0 + i] = s;
     });
     tpe_arm_mulM<S, T, B1>(e, x, out);
@@ -124,15 +136,28 @@ template <class S, typename T, class E> struct TpeSolver {
   E& e;
   const Model<S, T>& m;
   int nc, base;
-  KM_HD TpeSolver(E& e_, const Model<S, T>& m_) : e(e_), m(m_), nc(e_.ncon), base(D::NFRIC + e_.nlim) {}
+  // joints whose limit row is active / whose active row has J = -e, gathered once per solve: every routine below walks
+  // the joints, and testing a register bit replaces the dof_lim[j] (and efc_desc) loads from the env record -- most
+  // joints are away from their limits
+  unsigned limmask, negmask;
+  KM_HD TpeSolver(E& e_, const Model<S, T>& m_) : e(e_), m(m_), nc(e_.ncon), base(D::NFRIC + e_.nlim), limmask(0), negmask(0) {
+    for (int j = 0; j < NVA; j++) {
+      const int r = e.dof_lim[j];
+      if (r >= 0) {
+        limmask |= 1u << j;
+        if (efc_neg(e.efc_desc[r])) negmask |= 1u << j;
+      }
+    }
+  }
+  KM_HD bool lim_on(int j) const { return (limmask >> j) & 1u; }
 
   KM_HD void mulM(const T* x, T* out) const { tpe_mulM<S, T>(e, m, x, out); }
-  KM_HD T lim_sign(int j) const { return efc_neg(e.efc_desc[e.dof_lim[j]]) ? T(-1) : T(1); }
+  KM_HD T lim_sign(int j) const { return ((negmask >> j) & 1u) ? T(-1) : T(1); }
 
   // J x without the reference acceleration: friction rows, limit rows (signed), contact base rows
   KM_HD void rows(const T* x, T* xf, T* xl, T (*xb)[4]) const {
     sfor<0, NF>([&](auto R) { constexpr int r = decltype(R)::value; constexpr int d = fric_dof_of<S>(r); xf[r] = x[d]; });
-    for (int j = 0; j < NVA; j++) xl[j] = e.dof_lim[j] >= 0 ? lim_sign(j) * x[j] : T(0);
+    for (int j = 0; j < NVA; j++) xl[j] = lim_on(j) ? lim_sign(j) * x[j] : T(0);
     for (int c = 0; c < nc; c++)
       for (int b = 0; b < 4; b++) xb[c][b] = brow(c, b, x);
   }
@@ -159,13 +184,13 @@ template <class S, typename T, class E> struct TpeSolver {
       c += fric_cost(a[d] - e.efc_aref[r], m.fr_D[r], m.fr_Rf[r], m.fr_loss[r], &f);
     });
     for (int j = 0; j < NVA; j++) {
-      const int r = e.dof_lim[j];
-      if (r >= 0) c += uni_cost(lim_sign(j) * a[j] - e.efc_aref[r], e.efc_D[r], &f);
+      if (lim_on(j)) { const int r = e.dof_lim[j]; c += uni_cost(lim_sign(j) * a[j] - e.efc_aref[r], e.efc_D[r], &f); }
     }
     for (int ci = 0; ci < nc; ci++) {
       T pb[4];
       for (int b = 0; b < 4; b++) pb[b] = brow(ci, b, a);
       const T Dc = e.con_D[ci];
+      KM_K_LOOP
       for (int k = 0; k < 3; k++) {
         const T tk = e.con_mu[ci][k] * pb[1 + k];
         c += uni_cost(pb[0] + tk - e.efc_aref[base + 6 * ci + 2 * k], Dc, &f);
@@ -191,16 +216,16 @@ template <class S, typename T, class E> struct TpeSolver {
     });
     sfor<0, NVA>([&](auto Jj) {
       constexpr int j = decltype(Jj)::value;
-      const int r = e.dof_lim[j];
-      if (r >= 0) {
+      if (lim_on(j)) {
         T f;
-        c += uni_cost(t.jar_l[j], e.efc_D[r], &f);
+        c += uni_cost(t.jar_l[j], e.efc_D[e.dof_lim[j]], &f);
         qfc[j] += lim_sign(j) * f;
       }
     });
     for (int ci = 0; ci < nc; ci++) {
       const T Dc = e.con_D[ci], p0 = t.jarb[ci][0];
       T fb[4] = {0, 0, 0, 0};
+      KM_K_LOOP
       for (int k = 0; k < 3; k++) {
         const T mu = e.con_mu[ci][k], tk = mu * t.jarb[ci][1 + k];
         T fp, fn;
@@ -245,8 +270,7 @@ template <class S, typename T, class E> struct TpeSolver {
     });
     sfor<0, NVA>([&](auto Jj) {
       constexpr int j = decltype(Jj)::value;
-      const int r = e.dof_lim[j];
-      if (r >= 0 && t.jar_l[j] < T(0)) hd[j] += e.efc_D[r];
+      if (lim_on(j) && t.jar_l[j] < T(0)) hd[j] += e.efc_D[e.dof_lim[j]];
     });
     // cube block first: C = diag + sum over ALL contacts of Jq^T W Jq, right-hand side g_c
     T Hc[21], xc[6];
@@ -376,6 +400,7 @@ template <class S, typename T, class E> struct TpeSolver {
     auto& t = e.t;
     const T Dc = e.con_D[ci], p0 = t.jarb[ci][0];
     T n = 0;
+    KM_K_LOOP
     for (int k = 0; k < 3; k++) {
       const T mu = e.con_mu[ci][k], tk = mu * t.jarb[ci][1 + k];
       const T p = p0 + tk - e.efc_aref[base + 6 * ci + 2 * k] < T(0) ? T(1) : T(0);
@@ -414,14 +439,14 @@ template <class S, typename T, class E> struct TpeSolver {
 #pragma unroll 1
 #endif
     for (int j = 0; j < NVA; j++) {
-      const int r = e.dof_lim[j];
-      if (r >= 0) {
+      if (lim_on(j)) {
         const T jv = t.jv_l[j], jar = t.jar_l[j];
-        if (jar + alpha * jv < T(0)) { const T Dr = e.efc_D[r]; q1 += Dr * jar * jv; q2 += T(0.5) * Dr * jv * jv; }
+        if (jar + alpha * jv < T(0)) { const T Dr = e.efc_D[e.dof_lim[j]]; q1 += Dr * jar * jv; q2 += T(0.5) * Dr * jv * jv; }
       }
     }
     for (int ci = 0; ci < nc; ci++) {
       const T Dc = e.con_D[ci], a0 = t.jarb[ci][0], v0 = t.jvb[ci][0];
+      KM_K_LOOP
       for (int k = 0; k < 3; k++) {
         const T mu = e.con_mu[ci][k], ak = mu * t.jarb[ci][1 + k], vk = mu * t.jvb[ci][1 + k];
         const T jarp = a0 + ak - e.efc_aref[base + 6 * ci + 2 * k], jvp = v0 + vk;
@@ -490,7 +515,7 @@ template <class S, typename T, class E> struct TpeSolver {
     mulM(e.qacc, t.Ma);
     rows(e.qacc, t.jar_f, t.jar_l, t.jarb);
     sfor<0, NF>([&](auto R) { t.jar_f[decltype(R)::value] -= e.efc_aref[decltype(R)::value]; });
-    for (int j = 0; j < NVA; j++) if (e.dof_lim[j] >= 0) t.jar_l[j] -= e.efc_aref[e.dof_lim[j]];
+    for (int j = 0; j < NVA; j++) if (lim_on(j)) t.jar_l[j] -= e.efc_aref[e.dof_lim[j]];
     const T scale = T(1) / (m.meaninertia * T(NV));
     T cost = update();
     int niter = 0;
