@@ -162,10 +162,19 @@ template <class S, typename T, class E> struct TpeSolver {
       for (int b = 0; b < 4; b++) xb[c][b] = brow(c, b, x);
   }
   // base row b of contact c times a dof-space vector: cube columns always, arm columns for finger-pad contacts
+  // A table-corner contact has the fixed frame of the plane normal (0,0,1): normal (0,0,1), tangents (0,1,0) and
+  // (-1,0,0) (makeframe), so the cube-translation columns of its four base rows are the exact constants 0 / +-1
+  // (make_constraint forms them as dot products with unit vectors).  Using the constants instead of loading those
+  // twelve words gives bit-identical sums and takes them out of the solver's hot set in local memory.
   KM_HD T brow(int c, int b, const T* x) const {
     T s = 0;
-    for (int k = 0; k < 6; k++) s += e.Jq[c][b][k] * x[NVA + k];
     const int sl = e.con_slot[c];
+    if (sl >= D::NPAD) {
+      s = b == 0 ? x[NVA + 2] : (b == 1 ? x[NVA + 1] : (b == 2 ? -x[NVA] : T(0)));
+      for (int k = 3; k < 6; k++) s += e.Jq[c][b][k] * x[NVA + k];
+      return s;
+    }
+    for (int k = 0; k < 6; k++) s += e.Jq[c][b][k] * x[NVA + k];
     if (sl < D::NPAD) {
       const unsigned sup = e.con_sup[c];
       for (int j = 0; j < NVA; j++) if ((sup >> j) & 1u) s += e.Ja[sl][b][j] * x[j];
@@ -234,11 +243,21 @@ template <class S, typename T, class E> struct TpeSolver {
         fb[0] += fp + fn;
         fb[1 + k] = mu * (fp - fn);
       }
-      sfor<0, 6>([&](auto K) {
-        constexpr int k = decltype(K)::value;
-        qfc[NVA + k] += e.Jq[ci][0][k] * fb[0] + e.Jq[ci][1][k] * fb[1] + e.Jq[ci][2][k] * fb[2] + e.Jq[ci][3][k] * fb[3];
-      });
       const int sl = e.con_slot[ci];
+      if (sl >= D::NPAD) {   // table corner: constant translation columns (see brow)
+        qfc[NVA + 0] += -fb[2];
+        qfc[NVA + 1] += fb[1];
+        qfc[NVA + 2] += fb[0];
+        sfor<3, 6>([&](auto K) {
+          constexpr int k = decltype(K)::value;
+          qfc[NVA + k] += e.Jq[ci][0][k] * fb[0] + e.Jq[ci][1][k] * fb[1] + e.Jq[ci][2][k] * fb[2] + e.Jq[ci][3][k] * fb[3];
+        });
+      } else {
+        sfor<0, 6>([&](auto K) {
+          constexpr int k = decltype(K)::value;
+          qfc[NVA + k] += e.Jq[ci][0][k] * fb[0] + e.Jq[ci][1][k] * fb[1] + e.Jq[ci][2][k] * fb[2] + e.Jq[ci][3][k] * fb[3];
+        });
+      }
       if (sl < D::NPAD) {
         const unsigned sup = e.con_sup[ci];
         sfor<0, NVA>([&](auto Jj) {
@@ -284,9 +303,13 @@ template <class S, typename T, class E> struct TpeSolver {
       T w00, w0[3], wk[3];
       contact_weights(ci, &w00, w0, wk);
       T Jr[4][6], Y[4][6];
+      const bool corner = e.con_slot[ci] >= D::NPAD;   // table corner: constant translation columns (see brow)
       sfor<0, 6>([&](auto K) {
         constexpr int k = decltype(K)::value;
-        for (int b = 0; b < 4; b++) Jr[b][k] = e.Jq[ci][b][k];
+        if (k < 3 && corner) {
+          Jr[0][k] = k == 2 ? T(1) : T(0); Jr[1][k] = k == 1 ? T(1) : T(0); Jr[2][k] = k == 0 ? T(-1) : T(0); Jr[3][k] = T(0);
+        } else
+          for (int b = 0; b < 4; b++) Jr[b][k] = e.Jq[ci][b][k];
         Y[0][k] = w00 * Jr[0][k] + w0[0] * Jr[1][k] + w0[1] * Jr[2][k] + w0[2] * Jr[3][k];
         for (int b = 1; b < 4; b++) Y[b][k] = w0[b - 1] * Jr[0][k] + wk[b - 1] * Jr[b][k];
       });
