@@ -140,7 +140,8 @@ template <class S, typename T, class E> struct TpeSolver {
   // the joints, and testing a register bit replaces the dof_lim[j] (and efc_desc) loads from the env record -- most
   // joints are away from their limits
   unsigned limmask, negmask;
-  KM_HD TpeSolver(E& e_, const Model<S, T>& m_) : e(e_), m(m_), nc(e_.ncon), base(D::NFRIC + e_.nlim), limmask(0), negmask(0) {
+  int evals;   // line-search evaluations of this solve (added to the env's diagnostic counter once, at the end)
+  KM_HD TpeSolver(E& e_, const Model<S, T>& m_) : e(e_), m(m_), nc(e_.ncon), base(D::NFRIC + e_.nlim), limmask(0), negmask(0), evals(0) {
     for (int j = 0; j < NVA; j++) {
       const int r = e.dof_lim[j];
       if (r >= 0) {
@@ -150,6 +151,9 @@ template <class S, typename T, class E> struct TpeSolver {
     }
   }
   KM_HD bool lim_on(int j) const { return (limmask >> j) & 1u; }
+  // friction coefficients of contact c: the model's (shared memory) -- make_constraint copies exactly these into
+  // e.con_mu, and reading them there would be three more local-memory words per contact in every routine
+  KM_HD const T* mu_of(int c) const { const int sl = e.con_slot[c]; return sl < D::NPAD ? m.pad_mu[sl] : m.tab_mu; }
 
   KM_HD void mulM(const T* x, T* out) const { tpe_mulM<S, T>(e, m, x, out); }
   KM_HD T lim_sign(int j) const { return ((negmask >> j) & 1u) ? T(-1) : T(1); }
@@ -199,9 +203,10 @@ template <class S, typename T, class E> struct TpeSolver {
       T pb[4];
       for (int b = 0; b < 4; b++) pb[b] = brow(ci, b, a);
       const T Dc = e.con_D[ci];
+      const T* mu3 = mu_of(ci);
       KM_K_LOOP
       for (int k = 0; k < 3; k++) {
-        const T tk = e.con_mu[ci][k] * pb[1 + k];
+        const T tk = mu3[k] * pb[1 + k];
         c += uni_cost(pb[0] + tk - e.efc_aref[base + 6 * ci + 2 * k], Dc, &f);
         c += uni_cost(pb[0] - tk - e.efc_aref[base + 6 * ci + 2 * k + 1], Dc, &f);
       }
@@ -233,10 +238,11 @@ template <class S, typename T, class E> struct TpeSolver {
     });
     for (int ci = 0; ci < nc; ci++) {
       const T Dc = e.con_D[ci], p0 = t.jarb[ci][0];
+      const T* mu3 = mu_of(ci);
       T fb[4] = {0, 0, 0, 0};
       KM_K_LOOP
       for (int k = 0; k < 3; k++) {
-        const T mu = e.con_mu[ci][k], tk = mu * t.jarb[ci][1 + k];
+        const T mu = mu3[k], tk = mu * t.jarb[ci][1 + k];
         T fp, fn;
         c += uni_cost(p0 + tk - e.efc_aref[base + 6 * ci + 2 * k], Dc, &fp);
         c += uni_cost(p0 - tk - e.efc_aref[base + 6 * ci + 2 * k + 1], Dc, &fn);
@@ -422,10 +428,11 @@ template <class S, typename T, class E> struct TpeSolver {
   KM_HD void contact_weights(int ci, T* w00, T* w0, T* wk) const {
     auto& t = e.t;
     const T Dc = e.con_D[ci], p0 = t.jarb[ci][0];
+    const T* mu3 = mu_of(ci);
     T n = 0;
     KM_K_LOOP
     for (int k = 0; k < 3; k++) {
-      const T mu = e.con_mu[ci][k], tk = mu * t.jarb[ci][1 + k];
+      const T mu = mu3[k], tk = mu * t.jarb[ci][1 + k];
       const T p = p0 + tk - e.efc_aref[base + 6 * ci + 2 * k] < T(0) ? T(1) : T(0);
       const T q = p0 - tk - e.efc_aref[base + 6 * ci + 2 * k + 1] < T(0) ? T(1) : T(0);
       n += p + q;
@@ -469,9 +476,10 @@ template <class S, typename T, class E> struct TpeSolver {
     }
     for (int ci = 0; ci < nc; ci++) {
       const T Dc = e.con_D[ci], a0 = t.jarb[ci][0], v0 = t.jvb[ci][0];
+      const T* mu3 = mu_of(ci);
       KM_K_LOOP
       for (int k = 0; k < 3; k++) {
-        const T mu = e.con_mu[ci][k], ak = mu * t.jarb[ci][1 + k], vk = mu * t.jvb[ci][1 + k];
+        const T mu = mu3[k], ak = mu * t.jarb[ci][1 + k], vk = mu * t.jvb[ci][1 + k];
         const T jarp = a0 + ak - e.efc_aref[base + 6 * ci + 2 * k], jvp = v0 + vk;
         const T jarn = a0 - ak - e.efc_aref[base + 6 * ci + 2 * k + 1], jvn = v0 - vk;
         if (jarp + alpha * jvp < T(0)) { q1 += Dc * jarp * jvp; q2 += T(0.5) * Dc * jvp * jvp; }
@@ -482,7 +490,7 @@ template <class S, typename T, class E> struct TpeSolver {
     q2 += qg2;
     *d1 = T(2) * alpha * q2 + q1;
     *d2 = T(2) * q2;
-    e.ls_evals++;
+    evals++;
   }
 
   // exact line search; returns the step (0: no progress possible).  One ls_eval site shared by all phases.
@@ -561,6 +569,7 @@ template <class S, typename T, class E> struct TpeSolver {
       }
     }
     for (int i = 0; i < NV; i++) e.warm[i] = e.qacc[i];
+    e.ls_evals += evals;
 #ifdef KM_TPE_DEBUG
     e.solver_niter += niter + (e.coupled ? 65536 : 0);   // debug build: totals over the env step
 #else
