@@ -259,7 +259,9 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   // memory beyond that (its launch time no longer hangs on single slow envs, and it issues ~7x fewer instructions).
   const int per_sm = (n_envs + h->num_sms - 1) / h->num_sms;
   int rc;
-  const int tpe_from = h->vt.nv > 16 ? 48 : 96;   // envs per SM from which the thread-per-env kernel wins (dual-arm / torso: 48)
+  // envs per SM from which the thread-per-env kernel wins (measured crossovers after the solver's hot-set work: solo arm
+  // between 55 and 69 envs per SM, dual-arm / torso between 28 and 41; profiles/r01_notes.md)
+  const int tpe_from = h->vt.nv > 16 ? 40 : 68;
   if (per_sm >= tpe_from && h->ik_mode != 1) rc = configure(h, 2, 0);   // the exact-parity IK mode lives in the lane-group kernels
   else {
     h->G = 32;
