@@ -17,7 +17,7 @@ EXPORTS = [
     "km_last_error", "km_version", "km_measure_fma_peak", "km_create", "km_destroy", "km_nq", "km_nv", "km_nu", "km_nmocap", "km_obs_dim",
     "km_act_dim", "km_state_dim", "km_max_contacts", "km_num_envs", "km_dtype", "km_configure", "km_launch_count",
     "km_launch_config", "km_reset", "km_step", "km_get_state", "km_set_state", "km_state_ptr", "km_contacts",
-    "km_solver_stats", "km_site_poses", "km_n_arm", "km_reset_host", "km_step_host",
+    "km_solver_stats", "km_debug_phase_clocks", "km_site_poses", "km_n_arm", "km_reset_host", "km_step_host",
     "km_render", "km_render_host", "km_render_record_floats", "km_get_render_records",
 ]
 
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
     L.km_state_ptr.restype = vp
     L.km_contacts.argtypes = [vp, vp, vp, vp]
     L.km_solver_stats.argtypes = [vp, vp, vp, vp]
+    L.km_debug_phase_clocks.argtypes = [vp, vp]
     L.km_site_poses.argtypes = [vp, vp, vp, vp]
     L.km_n_arm.argtypes = [vp]
     L.km_reset_host.argtypes = [vp, vp, vp, vp]

@@ -31,6 +31,7 @@ struct km_sim {
   void* d_model;
   void* d_state;
   int *d_step, *d_episode, *d_niter, *d_ls;
+  unsigned* d_clk;   // caller-owned buffer of km_debug_phase_clocks (debug builds)
   // staging for the host-buffer entry points
   float* d_act;
   void *d_obs, *d_reward, *d_xyz;
@@ -147,7 +148,7 @@ static KmArgs base_args(km_sim* h, void* stream) {
   KmArgs a;
   std::memset(&a, 0, sizeof(a));
   a.model = h->d_model; a.state = h->d_state; a.step = h->d_step; a.episode = h->d_episode;
-  a.niter = h->d_niter; a.ls = h->d_ls;
+  a.niter = h->d_niter; a.ls = h->d_ls; a.clk = h->d_clk;
   a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid; a.lpw = h->lpw > 0 ? h->lpw : 32; a.tpl_small_regs = h->tpl_ctas > 1;
   a.stream = (cudaStream_t)stream;
   return a;
@@ -386,6 +387,17 @@ int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream
   if (niter_dev) KM_CUDA(cudaMemcpyAsync(niter_dev, h->d_niter, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
   if (ls_evals_dev) KM_CUDA(cudaMemcpyAsync(ls_evals_dev, h->d_ls, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
   return KM_OK;
+}
+
+int km_debug_phase_clocks(km_handle h, unsigned* clk_dev) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+#ifdef KM_PHASE_CLOCKS
+  h->d_clk = clk_dev;
+  return KM_OK;
+#else
+  (void)clk_dev;
+  return fail(KM_ERR_ARG, "km_debug_phase_clocks: the library was built without -DKM_PHASE_CLOCKS");
+#endif
 }
 
 int km_render(km_handle h, const km_camera* cam, const km_visual* vis, unsigned char* rgb_dev, void* stream) {

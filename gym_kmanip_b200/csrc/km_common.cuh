@@ -17,9 +17,20 @@
 #if defined(__CUDACC__)
 #define KM_HD __host__ __device__ __forceinline__
 #define KM_FN __host__ __device__ __noinline__
+#define KM_DI __device__ __forceinline__
+#define KM_DN __device__ __noinline__
 #else
 #define KM_HD inline
 #define KM_FN
+#define KM_DI inline
+#define KM_DN
+#endif
+// Warp-collective code paths: the device, or the host emulation of one warp that tests/hostsim/warpemu.h provides (it
+// defines KM_WARP_EMU and the __shfl_sync / __ballot_sync / __syncwarp ... intrinsics before including this file)
+#if defined(__CUDA_ARCH__) || defined(KM_WARP_EMU)
+#define KM_WARP_CODE 1
+#else
+#define KM_WARP_CODE 0
 #endif
 
 namespace km {
@@ -104,12 +115,12 @@ template <int G> struct Grp {
   // G == 1 is the thread-per-env mapping: every thread owns an env, so all group collectives are identities and
   // nothing may synchronise with other threads (their control flow is independent).
   KM_HD void converge() const {
-#if defined(__CUDA_ARCH__)
+#if KM_WARP_CODE
     if (G > 1 && G < 32) __syncwarp(wmask);
 #endif
   }
   template <typename T> KM_HD T shfl(T v, int src) const {
-#if defined(__CUDA_ARCH__)
+#if KM_WARP_CODE
     if (G == 1) return v;
     return __shfl_sync(lanes(), v, src, G);
 #else
@@ -120,15 +131,18 @@ template <int G> struct Grp {
   // sub-step together makes the warps of an SM fetch the same instructions at the same time: the hot loop is far
   // larger than the 32 KB L1.5 instruction cache, and unaligned warps spent over half their stall time waiting for
   // instruction fetch.  Only called from code every thread of the CTA executes the same number of times.
-  // KM_LOCKSTEP: 2 = phases and Newton iterations CTA-wide, 1 = phases only, 0 = warps run free
+  // KM_LOCKSTEP: 2 = phases and Newton iterations CTA-wide (generic solver only: every warp of the CTA must run it),
+  // 1 = phases only (default: the register-resident solver of km_solver_warp.cuh is small enough for the cache), 0 = warps run free
 #ifndef KM_LOCKSTEP
-#define KM_LOCKSTEP 2
+#define KM_LOCKSTEP 1
 #endif
   // (thread-per-env groups set wmask = ~0u to ask for the phase alignment: there every thread of the CTA runs the
   // same number of env steps, shadowing a valid env where the batch ends)
   KM_HD void cta_sync() const {
 #if defined(__CUDA_ARCH__)
     if (G > 1 ? KM_LOCKSTEP >= 1 : wmask == 0xffffffffu) __syncthreads();
+#elif defined(KM_WARP_EMU)
+    if (G > 1) __syncwarp(0xffffffffu);   // the emulated CTA is one warp
 #endif
   }
   KM_HD bool cta_any(bool p) const {
@@ -136,24 +150,29 @@ template <int G> struct Grp {
     if (G == 1) return p;
     if (KM_LOCKSTEP < 2) return (__ballot_sync(0xffffffffu, p) != 0u);
     return __syncthreads_or(p) != 0;
+#elif defined(KM_WARP_EMU)
+    if (G == 1) return p;
+    return __ballot_sync(0xffffffffu, p) != 0u;
 #else
     return p;
 #endif
   }
   KM_HD void sync() const {
-#if defined(__CUDA_ARCH__)
+#if KM_WARP_CODE
     if (G > 1) __syncwarp(lanes());
 #endif
   }
   template <typename T> KM_HD T sum(T v) const {
-#if defined(__CUDA_ARCH__)
+#if KM_WARP_CODE
+    if (G > 1) {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(lanes(), v, o, G);
+      for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(lanes(), v, o, G);
+    }
 #endif
     return v;
   }
   KM_HD bool any(bool p) const {
-#if defined(__CUDA_ARCH__)
+#if KM_WARP_CODE
     if (G == 1) return p;
     return (__ballot_sync(lanes(), p) & lanes()) != 0u;
 #else
@@ -162,6 +181,14 @@ template <int G> struct Grp {
   }
 };
 #define KM_FOR(i, n) for (int i = g.lane; i < (n); i += G)
+// Debug build (-DKM_PHASE_CLOCKS): lane 0 charges the cycles since the previous mark to phase `id` (km_debug_phase_clocks)
+#if defined(KM_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define KM_CLK(id) do { if (g.lane == 0) { const unsigned t__ = (unsigned)clock(); e.clk[id] += t__ - e.clk_last; e.clk_last = t__; } } while (0)
+#else
+#define KM_CLK(id) do {} while (0)
+#endif
+enum { CLK_KIN = 0, CLK_CRB, CLK_COLL, CLK_VEL, CLK_ACC, CLK_SOL_SETUP, CLK_SOL_DIR, CLK_SOL_LS, CLK_SOL_UPD, CLK_SOL_VOTE, CLK_EULER,
+       CLK_BARRIER, CLK_BEFORE, CLK_EPILOGUE, CLK_N };
 
 // compile-time loops (bodies receive std::integral_constant so indices can select registers / if constexpr)
 template <int I> using IC = std::integral_constant<int, I>;

@@ -116,6 +116,14 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
   }
   for (int i = 0, w = 0; i < D::NV; i++)
     for (int j = 0; j <= i; j++) m.pair_ij[w++] = (unsigned short)(i << 8 | j);
+  for (int j = 0; j < D::NV; j++) {   // blocks = kinematic chains (links sharing a root), then the cube
+    int r = j;
+    while (r < D::NVA && m.parent[r] >= 0) r = m.parent[r];
+    int e = j + 1;
+    if (j >= D::NVA) { r = D::NVA; e = D::NV; }
+    else while (e < D::NVA) { int q = e; while (m.parent[q] >= 0) q = m.parent[q]; if (q != r) break; e++; }
+    m.blk0[j] = r; m.blkn[j] = e - r;
+  }
   int maxd = 0;
   for (int l = 0; l < D::NVA; l++) maxd = depth[l] > maxd ? depth[l] : maxd;
   KM_FILL_CHECK(maxd + 1 <= D::MAXLEVEL, "kinematic tree too deep");

@@ -29,6 +29,7 @@ struct KmArgs {
   int* con_geoms;
   int* niter;
   int* ls;
+  unsigned* clk;   // debug build (KM_PHASE_CLOCKS): per-env phase cycles of the step
   const unsigned char* mask;
   const void* cube_xyz;
   void* site_pos;
@@ -109,7 +110,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
   const int slot = threadIdx.x / G;
   Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
   init_env<S, T, G>(e, m, g);
-  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON};
+  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON, a.clk};
   // every warp walks the same number of tiles so that the groups sharing a warp can reconverge
   for (long tile = (long)blockIdx.x * a.epb; tile < a.n; tile += (long)gridDim.x * a.epb) {
     const long env = tile + slot;
@@ -120,7 +121,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
     }
     // env slots past the end of the batch shadow the tile's first env (the CTA marches in phase) and store nothing
     const long envc = valid ? env : tile;
-    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON};
+    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr};
     load_state<S, T, G>(e, a, envc, g);
     env_step<S, T, G>(e, m, g, a.act + envc * m.act_dim, valid ? o : none, envc, a.autoreset, a.seed, a.env0);
     if (valid) {
@@ -161,13 +162,13 @@ template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __lau
   E e_local;
   E& e = LOCAL ? e_local : *(E*)(smem + model_smem<S, T>() + (size_t)threadIdx.x * Tpe<S, T>::stride);
   init_env<S, T, 1>(e, m, g);
-  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON};
+  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON, a.clk};
   if (LOCAL) {
     // Every thread of the CTA walks the same number of tiles, and the warps of the CTA are kept in the same phase of
     // the sub-step by CTA barriers (the sub-step body is far larger than the instruction cache); threads past the end
     // of the batch shadow the tile's first env and store nothing.
     g.wmask = 0xffffffffu;
-    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON};
+    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr};
     const long tiles = ((long)a.n + a.epb - 1) / a.epb;
     for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       // envs of the tile are dealt to the warps lpw at a time: with few envs per SM every scheduler still gets a

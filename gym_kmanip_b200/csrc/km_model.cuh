@@ -61,6 +61,7 @@ template <class S, typename T> struct Model {
   int parent[D::NVA], jtype[D::NVA], sub_end[D::NVA];
   unsigned ancmask[D::NVA];                       // bit j set: dof j is l or an ancestor of l
   unsigned short pair_ij[D::NV * (D::NV + 1) / 2]; // lower-triangle work list: i << 8 | j
+  int blk0[D::NV], blkn[D::NV];                   // diagonal block of the mass matrix that dof j lies in: first dof, size
   int nlevel, level_adr[D::MAXLEVEL + 1], level_link[D::NVA];
   T lpos[D::NVA][3], lquat[D::NVA][4];            // pose in the parent link, or in the world when parent < 0
   T mass[D::NVA], ipos[D::NVA][3], inertia[D::NVA][3];
@@ -133,6 +134,9 @@ template <class S, typename T, bool TPE_ = false> struct Env {
   T bias[D::NV], qfrc_smooth[D::NV], qacc_smooth[D::NV], qacc[D::NV];
   T obs[D::OBS];
   int solver_niter, ls_evals;                     // diagnostics of the last sub-step
+#ifdef KM_PHASE_CLOCKS
+  unsigned clk[16], clk_last;                     // debug build: cycles per phase of the current env step (KM_CLK)
+#endif
   // Scratch that is live in disjoint phases shares storage:
   //   a: position/velocity stage (step1)   b: IK between step1 and step2   c: Newton solver (step2)
   struct StageA {

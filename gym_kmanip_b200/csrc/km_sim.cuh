@@ -157,7 +157,7 @@ template <class S, typename T, int G, bool DENSE, class E> KM_FN void solve_spd(
   typedef Dim<S> D;
   typedef Num<T> N;
   constexpr int NV = D::NV;
-#if defined(__CUDA_ARCH__)
+#if KM_WARP_CODE
   if constexpr (G > 1) {
   static_assert(G >= NV, "one lane per dof row");
   g.sync();
@@ -531,14 +531,20 @@ KM_TPL KM_FN void mul_M(KM_ARGS, const T* x, T* out) {
 KM_TPL KM_HD void fwd_position(KM_ARGS) {
   typedef Dim<S> D;
   g.cta_sync();
+  KM_CLK(CLK_BARRIER);
   kinematics<S, T, G>(e, m, g);
+  KM_CLK(CLK_KIN);
   g.cta_sync();
+  KM_CLK(CLK_BARRIER);
   com_crb<S, T, G>(e, m, g);
+  KM_CLK(CLK_CRB);
   g.cta_sync();
+  KM_CLK(CLK_BARRIER);
   collision<S, T, G>(e, m, g);
   make_constraint<S, T, G>(e, m, g);
   KM_FOR(i, D::NU) e.actlen[i] = e.qpos[i];   // mj_transmission: joint transmissions, gear 1
   g.sync();
+  KM_CLK(CLK_COLL);
 }
 
 // =========================================================================================== velocity stage
@@ -613,8 +619,8 @@ KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
 namespace km {
 
 // =========================================================================================== acceleration stage
-// mj_fwdActuation (<position kp> servos) + mj_fwdAcceleration.
-KM_TPL KM_FN void fwd_actuation_acceleration(KM_ARGS) {
+// mj_fwdActuation (<position kp> servos): qfrc_smooth = actuator force - bias
+KM_TPL KM_FN void fwd_actuation(KM_ARGS) {
   typedef Dim<S> D;
   KM_FOR(i, D::NV) {
     T f = 0;
@@ -622,13 +628,17 @@ KM_TPL KM_FN void fwd_actuation_acceleration(KM_ARGS) {
       const T c = tclip(e.ctrl[i], m.ctrl_lo[i], m.ctrl_hi[i]);
       f = tclip(m.kp[i] * c - m.kp[i] * e.actlen[i], m.frc_lo[i], m.frc_hi[i]);
     }
-    const T s = f - e.bias[i];
-    e.qfrc_smooth[i] = s;
-    if constexpr (G > 1) e.c.hdiag[i] = 0;
+    e.qfrc_smooth[i] = f - e.bias[i];
   }
   g.sync();
+}
+// mj_fwdAcceleration: qacc_smooth = M^{-1} qfrc_smooth
+KM_TPL KM_FN void fwd_acceleration(KM_ARGS) {
+  typedef Dim<S> D;
   if constexpr (G == 1) tpe_solveM<S, T>(e, m, e.qfrc_smooth, e.qacc_smooth);
   else {
+    KM_FOR(i, D::NV) e.c.hdiag[i] = 0;
+    g.sync();
     assemble_h<S, T, G>(e, m, g, false);
     solve_spd<S, T, G, false>(e, m, g, e.qfrc_smooth, e.qacc_smooth);
   }
@@ -795,6 +805,7 @@ KM_TPL KM_FN void fwd_constraint(KM_ARGS) {
   const T scale = T(1) / (m.meaninertia * T(D::NV));
   T gauss;
   T cost = sol_update<S, T, G>(e, m, g, &gauss);
+  KM_CLK(CLK_SOL_SETUP);
   int niter = 0;
   bool done = niter >= m.iterations;
   // Newton iterations, marched CTA-wide: envs that have converged idle at the vote until the slowest is done
@@ -803,7 +814,9 @@ KM_TPL KM_FN void fwd_constraint(KM_ARGS) {
       sol_hessian_dir<S, T, G>(e, m, g);
       KM_FOR(i, D::NV) e.c.search[i] = -e.c.Mgrad[i];
       g.sync();
+      KM_CLK(CLK_SOL_DIR);
       const T alpha = sol_linesearch<S, T, G>(e, m, g, scale);
+      KM_CLK(CLK_SOL_LS);
       if (alpha == T(0)) done = true;
       else {
         KM_FOR(i, D::NV) { e.qacc[i] += alpha * e.c.search[i]; e.c.Ma[i] += alpha * e.c.Mv[i]; }
@@ -816,15 +829,22 @@ KM_TPL KM_FN void fwd_constraint(KM_ARGS) {
         gn = g.sum(gn);
         niter++;
         done = scale * (oldcost - cost) < m.tol || scale * N::sqrt(gn) < m.tol || niter >= m.iterations;
+        KM_CLK(CLK_SOL_UPD);
       }
     }
-    if (!g.cta_any(!done)) break;
+    const bool more = g.cta_any(!done);
+    KM_CLK(CLK_SOL_VOTE);
+    if (!more) break;
   }
   g.converge();
   KM_FOR(i, D::NV) e.warm[i] = e.qacc[i];
   if (g.lane == 0) e.solver_niter = niter;
   g.sync();
 }
+
+}  // namespace km
+#include "km_solver_warp.cuh"
+namespace km {
 
 // mj_Euler (no joint damping anywhere): semi-implicit, free-joint quaternion integrated on the manifold (A6)
 KM_TPL KM_FN void euler(KM_ARGS) {
@@ -863,15 +883,36 @@ KM_TPL KM_FN void euler(KM_ARGS) {
 KM_TPL KM_HD void step1(KM_ARGS) {
   fwd_position<S, T, G>(e, m, g);
   g.cta_sync();
+  KM_CLK(CLK_BARRIER);
   fwd_velocity<S, T, G>(e, m, g);
+  KM_CLK(CLK_VEL);
 }
+// KM_WARP_SOLVER = 0 keeps the generic lane-group solver for every env (A/B experiments)
+#ifndef KM_WARP_SOLVER
+#define KM_WARP_SOLVER 1
+#endif
 KM_TPL KM_HD void step2(KM_ARGS) {
   g.cta_sync();
-  fwd_actuation_acceleration<S, T, G>(e, m, g);
+  KM_CLK(CLK_BARRIER);
+  fwd_actuation<S, T, G>(e, m, g);
+  KM_CLK(CLK_ACC);
   g.cta_sync();
-  if constexpr (G == 1) fwd_constraint_tpe<S, T>(e, m);
+  KM_CLK(CLK_BARRIER);
+#if KM_WARP_CODE && KM_WARP_SOLVER
+  if constexpr (G == 32) {
+    // register-resident solver (km_solver_warp.cuh) unless a finger pad touches the cube (arm and cube blocks couple)
+    if (!e.coupled) fwd_acc_constraint_w<S, T>(e, m, g);
+    else { fwd_acceleration<S, T, G>(e, m, g); fwd_constraint<S, T, G>(e, m, g); }
+    euler<S, T, G>(e, m, g);
+    KM_CLK(CLK_EULER);
+    return;
+  }
+#endif
+  fwd_acceleration<S, T, G>(e, m, g);
+  if constexpr (G == 1) { fwd_constraint_tpe<S, T>(e, m); KM_CLK(CLK_SOL_DIR); }
   else fwd_constraint<S, T, G>(e, m, g);
   euler<S, T, G>(e, m, g);
+  KM_CLK(CLK_EULER);
 }
 
 // =========================================================================================== task: action decode + IK
@@ -1237,15 +1278,21 @@ KM_TPL KM_FN void init_env(KM_ARGS) {
 template <typename T> struct StepOut {
   T* obs; T* final_obs; T* reward; unsigned char* truncated; unsigned char* terminated;
   int* con_flags; int* ncon; int* con_geoms; int con_cap;
+  unsigned* clk;   // debug build (KM_PHASE_CLOCKS): [n][16] cycles per phase of this env step
 };
 
 // One env step on the working set already holding the env's state.
 KM_TPL KM_FN void env_step(KM_ARGS, const float* act, const StepOut<T>& o, long env, int autoreset, uint64_t seed,
                            uint64_t env0) {
   typedef Dim<S> D;
+#if defined(KM_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+  if (g.lane == 0) { for (int i = 0; i < 16; i++) e.clk[i] = 0; e.clk_last = (unsigned)clock(); }
+#endif
   step1<S, T, G>(e, m, g);
   g.cta_sync();
+  KM_CLK(CLK_BARRIER);
   before_step<S, T, G>(e, m, g, act);
+  KM_CLK(CLK_BEFORE);
   step2<S, T, G>(e, m, g);
   for (int s = 1; s < m.nsub; s++) { step1<S, T, G>(e, m, g); step2<S, T, G>(e, m, g); }
   // closing mj_step1: only kinematics and collision feed the reward / contact report; the next env step
@@ -1285,6 +1332,10 @@ KM_TPL KM_FN void env_step(KM_ARGS, const float* act, const StepOut<T>& o, long 
     if (o.obs) KM_FOR(i, D::OBS) o.obs[env * D::OBS + i] = e.obs[i];
   }
   g.sync();
+  KM_CLK(CLK_EPILOGUE);
+#if defined(KM_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+  if (o.clk && g.lane == 0) for (int i = 0; i < 16; i++) o.clk[env * 16 + i] = e.clk[i];
+#endif
 }
 
 }  // namespace km

@@ -187,6 +187,11 @@ int km_get_render_records(km_handle h, float* recs_dev, void* stream);
 
 /* Diagnostics of the most recent step's last sub-step: [n] Newton iterations, [n] line-search evaluations (cumulative). */
 int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream);
+/* Profiling aid: after this call every km_step also writes [n][16] uint32 cycle counts per phase of the env step
+   (position stage, velocity stage, Newton solver pieces, barrier waits ...; enum CLK_* in csrc/km_common.cuh) into the
+   caller's device buffer; NULL switches it off.  Only libraries built with -DKM_PHASE_CLOCKS record anything; the
+   production build returns KM_ERR_ARG. */
+int km_debug_phase_clocks(km_handle h, unsigned* clk_dev);
 
 /* Host-buffer variants (pageable or pinned host memory; copies and a stream synchronise inside). */
 int km_reset_host(km_handle h, const unsigned char* mask, const void* cube_xyz, void* obs);

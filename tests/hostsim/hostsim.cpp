@@ -3,8 +3,14 @@
 // TEST INFRASTRUCTURE ONLY: lets tests run the identical simulator source on the CPU against the oracle while
 // no GPU is attached (stage-by-stage parity, fp32 and fp64).  It is not a product path: the package never
 // loads it, and the product fails loudly without the CUDA library.
+//
+// Two mappings: lanes = 1 runs the generic code with one lane per env (plain loops); lanes = 32 runs the warp-per-env
+// code -- including the register-resident solver of km_solver_warp.cuh with its shuffles and votes -- on the emulated
+// warp of warpemu.h, which also checks that the 32 lanes execute the same collectives in the same order.
 #include <cstring>
 #include <string>
+#define KM_WARP_EMU 1
+#include "warpemu.h"
 #include "../../gym_kmanip_b200/csrc/km_fill.h"
 
 using namespace km;
@@ -21,15 +27,32 @@ struct HostSimBase {
                         int* ncon, int* geoms, int autoreset, uint64_t seed, uint64_t env_id) = 0;
   virtual void reset(uint64_t seed, uint64_t env_id, const double* xyz, double* obs) = 0;
   virtual int field(const char* name, double* out, int cap) = 0;
+  std::string fault;   // set when the emulated warp's lanes diverged at a collective
 };
 
-template <class S, typename T> struct HostSim : HostSimBase {
+template <class S, typename T, int G> struct HostSim : HostSimBase {
   typedef Dim<S> D;
   Model<S, T> m;
   Env<S, T> e;
-  Grp<1> g;
-  HostSim() { g.lane = 0; g.mask = 1u; std::memset((void*)&e, 0, sizeof(e)); }
-  void init() { init_env<S, T, 1>(e, m, g); }
+  km_emu::Warp* warp;
+  HostSim() : warp(G == 32 ? new km_emu::Warp() : nullptr) { std::memset((void*)&e, 0, sizeof(e)); }
+  ~HostSim() override { delete warp; }
+  // run f(group) on the one lane (G = 1) or on the 32 lanes of the emulated warp
+  template <class F> void par(F f) {
+    if constexpr (G == 1) {
+      Grp<1> g;
+      g.lane = 0; g.mask = 1u; g.wmask = 1u;
+      f(g);
+    } else {
+      const bool ok = km_emu::run(*warp, [&](int lane) {
+        Grp<G> g;
+        g.lane = lane; g.mask = 0xffffffffu; g.wmask = 0xffffffffu;
+        f(g);
+      });
+      if (!ok && fault.empty()) fault = warp->error;
+    }
+  }
+  void init() { par([&](const Grp<G>& g) { init_env<S, T, G>(e, m, g); }); }
   int dims(int* out) override {
     out[0] = D::NQ; out[1] = D::NV; out[2] = D::NU; out[3] = D::NMOCAP; out[4] = D::OBS; out[5] = m.act_dim; out[6] = D::MAXCON;
     return 0;
@@ -57,24 +80,26 @@ template <class S, typename T> struct HostSim : HostSimBase {
     if (step) *step = e.step;
     if (episode) *episode = e.episode;
   }
-  void step1() override { km::step1<S, T, 1>(e, m, g); }
-  void step2() override { km::step2<S, T, 1>(e, m, g); }
-  void before_step(const float* act) override { km::before_step<S, T, 1>(e, m, g, act); }
+  void step1() override { par([&](const Grp<G>& g) { km::step1<S, T, G>(e, m, g); }); }
+  void step2() override { par([&](const Grp<G>& g) { km::step2<S, T, G>(e, m, g); }); }
+  void before_step(const float* act) override { par([&](const Grp<G>& g) { km::before_step<S, T, G>(e, m, g, act); }); }
   void env_step(const float* act, double* obs, double* final_obs, double* reward, unsigned char* trunc, int* flags, int* ncon,
                 int* geoms, int autoreset, uint64_t seed, uint64_t env_id) override {
     T o[D::OBS], fo[D::OBS], r = 0;
     for (int i = 0; i < D::OBS; i++) fo[i] = 0;
     unsigned char term = 0;
     StepOut<T> so = {o, fo, &r, trunc, &term, flags, ncon, geoms, D::MAXCON};
-    km::env_step<S, T, 1>(e, m, g, act, so, 0, autoreset, seed, env_id);
+    par([&](const Grp<G>& g) { km::env_step<S, T, G>(e, m, g, act, so, 0, autoreset, seed, env_id); });
     for (int i = 0; i < D::OBS; i++) { obs[i] = (double)o[i]; if (final_obs) final_obs[i] = (double)fo[i]; }
     *reward = (double)r;
   }
   void reset(uint64_t seed, uint64_t env_id, const double* xyz, double* obs) override {
     T c[3];
     if (xyz) for (int i = 0; i < 3; i++) c[i] = (T)xyz[i];
-    reset_state<S, T, 1>(e, m, g, seed, env_id, xyz ? c : (const T*)0);
-    observation<S, T, 1>(e, m, g);
+    par([&](const Grp<G>& g) {
+      reset_state<S, T, G>(e, m, g, seed, env_id, xyz ? c : (const T*)0);
+      observation<S, T, G>(e, m, g);
+    });
     if (obs) for (int i = 0; i < D::OBS; i++) obs[i] = (double)e.obs[i];
   }
   int field(const char* name, double* out, int cap) override {
@@ -122,10 +147,10 @@ template <class S, typename T> struct HostSim : HostSimBase {
     else if (s == "ncon") PUT(e.ncon);
     else if (s == "nefc") PUT(e.nefc);
     else if (s == "site_xpos") {
-      for (int a = 0; a < m.n_arm; a++) { T p[3], R[9]; site_pose<S, T, 1>(e, m, a, p, R); for (int i = 0; i < 3; i++) PUT(p[i]); }
+      for (int a = 0; a < m.n_arm; a++) { T p[3], R[9]; site_pose<S, T, G>(e, m, a, p, R); for (int i = 0; i < 3; i++) PUT(p[i]); }
     }
     else if (s == "site_xmat") {
-      for (int a = 0; a < m.n_arm; a++) { T p[3], R[9]; site_pose<S, T, 1>(e, m, a, p, R); for (int i = 0; i < 9; i++) PUT(R[i]); }
+      for (int a = 0; a < m.n_arm; a++) { T p[3], R[9]; site_pose<S, T, G>(e, m, a, p, R); for (int i = 0; i < 9; i++) PUT(R[i]); }
     }
     else if (s == "sizeof_env") PUT(sizeof(e));
     else if (s == "sizeof_model") PUT(sizeof(m));
@@ -137,26 +162,25 @@ template <class S, typename T> struct HostSim : HostSimBase {
 
 static thread_local std::string g_err;
 
-template <class S> static HostSimBase* make(const km_model* fm, const km_task* tk, int dtype) {
-  if (dtype == 32) {
-    auto* h = new HostSim<S, float>();
-    if (fill_model<S, float>(fm, tk, &h->m, g_err)) { delete h; return nullptr; }
-    h->init();
-    return h;
-  }
-  auto* h = new HostSim<S, double>();
-  if (fill_model<S, double>(fm, tk, &h->m, g_err)) { delete h; return nullptr; }
+template <class S, typename T, int G> static HostSimBase* make2(const km_model* fm, const km_task* tk) {
+  auto* h = new HostSim<S, T, G>();
+  if (fill_model<S, T>(fm, tk, &h->m, g_err)) { delete h; return nullptr; }
   h->init();
   return h;
+}
+template <class S> static HostSimBase* make(const km_model* fm, const km_task* tk, int dtype, int lanes) {
+  if (lanes == 32) return dtype == 32 ? make2<S, float, 32>(fm, tk) : make2<S, double, 32>(fm, tk);
+  return dtype == 32 ? make2<S, float, 1>(fm, tk) : make2<S, double, 1>(fm, tk);
 }
 
 extern "C" {
 const char* hs_last_error() { return g_err.c_str(); }
-void* hs_create(const km_model* fm, const km_task* tk, int scene, int dtype) {
+void* hs_create(const km_model* fm, const km_task* tk, int scene, int dtype, int lanes) {
+  if (lanes != 1 && lanes != 32) { g_err = "lanes must be 1 or 32"; return nullptr; }
   switch (scene) {
-    case 0: return make<SceneSoloArm>(fm, tk, dtype);
-    case 1: return make<SceneDualArm>(fm, tk, dtype);
-    case 2: return make<SceneTorso>(fm, tk, dtype);
+    case 0: return make<SceneSoloArm>(fm, tk, dtype, lanes);
+    case 1: return make<SceneDualArm>(fm, tk, dtype, lanes);
+    case 2: return make<SceneTorso>(fm, tk, dtype, lanes);
   }
   g_err = "unknown scene";
   return nullptr;
@@ -176,4 +200,6 @@ void hs_reset(void* h, unsigned long long seed, unsigned long long env_id, const
   ((HostSimBase*)h)->reset(seed, env_id, xyz, obs);
 }
 int hs_field(void* h, const char* name, double* out, int cap) { return ((HostSimBase*)h)->field(name, out, cap); }
+// non-empty when the lanes of the emulated warp diverged at a collective (a hang or undefined behaviour on the GPU)
+const char* hs_fault(void* h) { return ((HostSimBase*)h)->fault.c_str(); }
 }

@@ -19,7 +19,8 @@ from gym_kmanip_b200 import constants as K, flatmodel, mjcf   # noqa: E402
 
 _SO = os.path.join(_HERE, "_build", "libhostsim.so")
 _SRC = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_ROOT, "gym_kmanip_b200", "csrc", f) for f in
-                                                ("km_common.cuh", "km_model.cuh", "km_sim.cuh", "km_solver_tpe.cuh", "km_ik_trf.cuh", "km_fill.h")]
+                                                ("km_common.cuh", "km_model.cuh", "km_sim.cuh", "km_solver_tpe.cuh", "km_solver_warp.cuh", "km_ik_trf.cuh", "km_fill.h")] + \
+    [os.path.join(_HERE, "warpemu.h")]
 _LIB = None
 SCENE_ID = {"solo_arm": 0, "dual_arm": 1, "torso": 2}
 
@@ -27,8 +28,8 @@ SCENE_ID = {"solo_arm": 0, "dual_arm": 1, "torso": 2}
 def build(force=False):
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in _SRC):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-x", "c++", "-shared", "-ffp-contract=off", "-o", _SO,
-                               _SRC[0]])
+        subprocess.check_call(["g++", "-O2", "-g1", "-fPIC", "-std=c++17", "-x", "c++", "-shared", "-ffp-contract=off", "-o", _SO,
+                               _SRC[0], "-ldl"])
 
 
 def lib():
@@ -38,6 +39,7 @@ def lib():
         L = C.CDLL(_SO)
         L.hs_create.restype = C.c_void_p
         L.hs_last_error.restype = C.c_char_p
+        L.hs_fault.restype = C.c_char_p
         _LIB = L
     return _LIB
 
@@ -47,14 +49,15 @@ def _dp(a):
 
 
 class HostSim:
-    def __init__(self, env_id="KManipSoloArm", dtype=64, **task_kw):
+    def __init__(self, env_id="KManipSoloArm", dtype=64, lanes=1, **task_kw):
+        """lanes = 1: generic code, one lane per env; lanes = 32: the warp-per-env device code on an emulated warp."""
         self.kw = K.ENV_REGISTRY[env_id]
         self.scene = mjcf.scene_of_mjcf(self.kw["mjcf_filename"])
         self.flat = mjcf.load_flat(self.scene)
         self.pm = flatmodel.PackedModel(self.flat)
         self.task = flatmodel.make_task(self.flat, self.kw, **task_kw)
         self.L = lib()
-        h = self.L.hs_create(self.pm.ref(), C.byref(self.task), SCENE_ID[self.scene], dtype)
+        h = self.L.hs_create(self.pm.ref(), C.byref(self.task), SCENE_ID[self.scene], dtype, lanes)
         if not h:
             raise RuntimeError(self.L.hs_last_error().decode())
         self.h = C.c_void_p(h)
@@ -95,6 +98,10 @@ class HostSim:
         out = self.unpack(rec)
         out["step"], out["episode"] = s.value, e.value
         return out
+
+    def fault(self):
+        """Non-empty when the lanes of the emulated warp diverged at a collective (a hang on the GPU)."""
+        return self.L.hs_fault(self.h).decode()
 
     def step1(self):
         self.L.hs_step1(self.h)

@@ -1,0 +1,29 @@
+"""Per-phase cycle profile of the env-step kernel (needs a library built with -DKM_PHASE_CLOCKS, see csrc/Makefile `dbg`).
+usage: KMANIP_B200_LIB=gym_kmanip_b200/lib_dbg/libkmanip_b200.so python tools/phase_clocks_gpu.py [env] [n] [lanes] [epb]"""
+import sys, os
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, R)
+import torch
+from gym_kmanip_b200 import _lib
+from gym_kmanip_b200.batch_sim import BatchSim
+env = sys.argv[1] if len(sys.argv) > 1 else "KManipSoloArmQPos"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+epb = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+sim = BatchSim(env, n, dtype="float32", seed=0)
+if lanes or epb:
+    sim.configure(lanes, epb)
+print("launch", sim.launch_config())
+clk = torch.zeros(n, 16, dtype=torch.int32, device="cuda")
+_lib.check(sim.L.km_debug_phase_clocks(sim.h, clk.data_ptr()))
+sim.reset()
+gen = torch.Generator(device="cuda").manual_seed(1234)
+names = ["kin", "crb", "coll+mkc", "vel", "acc", "sol_setup", "sol_dir", "sol_ls", "sol_upd", "sol_vote", "euler", "barrier", "before", "epilogue"]
+for t in range(40):
+    act = torch.rand(n, sim.act_dim, device="cuda", generator=gen) * 2 - 1
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); sim.step(act, contacts=False); e1.record(); torch.cuda.synchronize()
+    if t in (3, 8, 15, 30, 39):
+        c = clk.cpu().double()
+        tot = c.sum(1)
+        print(f"step {t}: {e0.elapsed_time(e1):.3f} ms; cycles per env step (lane 0 of each env): mean total {tot.mean():.0f} max {tot.max():.0f}")
+        print("   " + "  ".join(f"{nm} {c[:, i].mean() / tot.mean() * 100:.1f}%" for i, nm in enumerate(names)))
