@@ -41,12 +41,12 @@ template <class S, typename T, class E> struct WarpSolver {
   const Model<S, T>& m;
   const Grp<32>& g;
   // roles
-  int lane, dofi, b0, bn, li, cl, cc, cb, ncon, ei, ej;
+  int lane, dofi, b0, bn, li, cl, cc, cb, ncon;
   bool isdof, isarm, iscube, iscon, isedge, has_f, has_l;
   // row constants: slot 0 = friction-loss row of the dof (or a pyramid edge on the solo-arm contact lanes), slot 1 = limit
-  T cdiag, rf0, fl0, sg, mu, Dr[NS], Jr[6];
+  T cdiag, rf0, fl0, sg, mu, Dr[NS];
   // solver state
-  T qacc, Ma, grad, search, Mv, qs, as, jar[NS], jv[NS], row[BS], dinv, hd_cached;
+  T qacc, Ma, grad, search, Mv, qs, as, jar[NS], jv[NS], dinv, hd_cached;
   int evals;
 
   KM_DI WarpSolver(E& e_, const Model<S, T>& m_, const Grp<32>& g_) : e(e_), m(m_), g(g_) {}
@@ -64,8 +64,10 @@ template <class S, typename T, class E> struct WarpSolver {
   // J x for this lane's rows (cube part of x in xs())
   KM_DI void jrows(T xi, T* out) const {
     T pb = 0;
+    const T* jr = e.Jq[iscon ? cc : 0][iscon ? cb : 0];
 #pragma unroll
-    for (int k = 0; k < 6; k++) pb += Jr[k] * xs()[NVA + k];
+    for (int k = 0; k < 6; k++) pb += jr[k] * xs()[NVA + k];
+    pb = iscon ? pb : T(0);
     const T p0 = __shfl_sync(0xffffffffu, pb, lane & ~3);
     out[0] = has_f ? xi : T(0);
     out[1] = has_l ? sg * xi : T(0);
@@ -117,19 +119,33 @@ template <class S, typename T, class E> struct WarpSolver {
   // sequence, so loops that contain shuffles are controlled by votes (warp-uniform by construction) and lanes without
   // a row carry dummy values instead of branching around the collective code.
   static constexpr unsigned FULL = 0xffffffffu;
+  // A zero the compiler cannot see through.  Shuffle source lanes (b0 + j) and similar per-lane constants are loop
+  // invariant, so ptxas hoists all of them out of the Newton loop into registers it does not have (the kernel runs 28
+  // warps per SM: 72 registers) and then spills other state to local memory, which thrashes the small L1 left beside the
+  // shared-memory carve-out.  Adding this zero inside the loop makes them cheap to recompute instead.
+  KM_DI int opaque_zero() const {
+#if defined(__CUDA_ARCH__)
+    int z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z));
+    return z;
+#else
+    return 0;
+#endif
+  }
   // Cholesky of every diagonal block at once: one lane per row, block-local columns in row[], pivots by shuffles
-  KM_DI void factor_blocks() {
-    const int bl = bn - 1;
+  // (columns past the end of a lane's block receive garbage from foreign lanes; nothing reads them)
+  KM_DI void factor_blocks(T* row) {
+    const int s0 = b0 + opaque_zero();
     sfor<0, BS>([&](auto J) {
       constexpr int j = decltype(J)::value;
-      const T ajj = __shfl_sync(FULL, row[j], b0 + (j < bl ? j : bl));
+      const T ajj = __shfl_sync(FULL, row[j], s0 + j);
       const T inv = N::rsqrt(tmax(ajj, N::minval()));
       const T lij = row[j] * inv;
       row[j] = lij;
       dinv = li == j ? inv : dinv;
       sfor<j + 1, BS>([&](auto K) {
         constexpr int k = decltype(K)::value;
-        row[k] -= lij * __shfl_sync(FULL, lij, b0 + (k < bl ? k : bl));
+        row[k] -= lij * __shfl_sync(FULL, lij, s0 + k);
       });
     });
   }
@@ -150,27 +166,30 @@ template <class S, typename T, class E> struct WarpSolver {
   }
   // x = H^{-1} rhs with the factor in row[] / dinv (the rows are also in e.c.H for the transposed access)
   KM_DI T solve(T rhs) const {
-    const int bl = bn - 1;
+    const int s0 = b0 + opaque_zero();
+    const T* hrow = e.c.H[dofi];                 // row i of the factor: L[i][j], j < li
+    const T* hcol = &e.c.H[b0][li];              // column li of the factor: L[b0 + j][li], j > li (row stride HS)
     T acc = rhs, y = 0;
     sfor<0, BS>([&](auto J) {
       constexpr int j = decltype(J)::value;
-      const T yj = __shfl_sync(FULL, acc * dinv, b0 + (j < bl ? j : bl));
+      const T yj = __shfl_sync(FULL, acc * dinv, s0 + j);
       y = li == j ? yj : y;
-      acc -= (li > j ? row[j] : T(0)) * yj;
+      const T l = hrow[j];
+      acc = li > j ? acc - l * yj : acc;         // (select, not a product with zero: yj of a foreign lane may be anything)
     });
     T acc2 = y, x = 0;
     sfor_rev<BS>([&](auto J) {
       constexpr int j = decltype(J)::value;
-      const T xj = __shfl_sync(FULL, acc2 * dinv, b0 + (j < bl ? j : bl));
+      const T xj = __shfl_sync(FULL, acc2 * dinv, s0 + j);
       x = li == j ? xj : x;
-      const T col = e.c.H[b0 + (j < bl ? j : bl)][li];
-      acc2 -= ((j > li && j < bn) ? col : T(0)) * xj;
+      const T l = hcol[(j < bn ? j : 0) * D::HS];
+      acc2 = (j > li && j < bn) ? acc2 - l * xj : acc2;
     });
     return x;
   }
-  // rows of the factor to e.c.H (lower triangle) for the lanes of `which`
-  KM_DI void store_rows(bool which) {
-    if (which) sfor<0, BS>([&](auto J) { constexpr int j = decltype(J)::value; if (j <= li) e.c.H[dofi][j] = row[j]; });
+  // rows of the factor (N block-local columns) to e.c.H (lower triangle) for the lanes of `which`
+  template <int N> KM_DI void store_rows(const T* row, bool which) {
+    sfor<0, N>([&](auto J) { constexpr int j = decltype(J)::value; if (which && j <= li) e.c.H[dofi][j] = row[j]; });
     g.sync();
   }
 
@@ -182,7 +201,9 @@ template <class S, typename T, class E> struct WarpSolver {
     const unsigned pm = __ballot_sync(FULL, isedge && (SH ? jar[EA] < T(0) : q0));
     const unsigned nm = __ballot_sync(FULL, isedge && (SH ? jar[EA + 1] < T(0) : q1));
     const bool refactor = __any_sync(FULL, isarm && hd != hd_cached);
-    // cube block: diag + sum over contacts of Jq^T W Jq, one lower-triangle entry per lane
+    // cube block: diag + sum over contacts of Jq^T W Jq, one lower-triangle entry (ei, ej) per lane
+    const int t = (lane < 21 ? lane : 20) + opaque_zero();
+    const int ei = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15), ej = t - ei * (ei + 1) / 2;
     const T hdi = __shfl_sync(FULL, hd, NVA + ei);
     if (lane < 21) {
       T h = ei == ej ? (ei < 3 ? m.cube_mass : m.cube_inertia[ei < 3 ? 0 : ei - 3]) + hdi : T(0);
@@ -207,18 +228,20 @@ template <class S, typename T, class E> struct WarpSolver {
     T w[6], dw = 1;
     sfor<0, 6>([&](auto J) { constexpr int j = decltype(J)::value; w[j] = e.c.H[iscube ? dofi : NVA][j]; });
     if (refactor) {   // warp-uniform (a vote): a friction-loss or limit row of the arm changed state
+      T row[BS], dsave = dinv;
       sfor<0, BS>([&](auto J) {
         constexpr int j = decltype(J)::value;
         const T mv = e.M[isarm ? dofi : 0][isarm ? b0 + (j < bn ? j : 0) : 0];
         row[j] = isarm ? (j < bn ? mv + (j == li ? hd : T(0)) : T(0)) : (j == li ? T(1) : T(0));
       });
       hd_cached = hd;
-      factor_blocks();
-      store_rows(isarm);
+      factor_blocks(row);
+      dinv = isarm ? dinv : dsave;
+      store_rows<BS>(row, isarm);
     }
     factor_cube(w, &dw);
-    if (iscube) { sfor<0, 6>([&](auto J) { constexpr int j = decltype(J)::value; row[j] = w[j]; }); dinv = dw; }
-    store_rows(iscube);
+    dinv = iscube ? dw : dinv;
+    store_rows<6>(w, iscube);
     { const T x = solve(grad); search = isdof ? -x : T(0); }   // every lane takes part in the shuffles
   }
 
@@ -301,7 +324,6 @@ template <class S, typename T, class E> struct WarpSolver {
     cl = lane - CL0; cc = (cl >> 2) & 3; cb = cl & 3;
     iscon = cl >= 0 && cl < 16 && cc < ncon;
     isedge = iscon && cb > 0;
-    { const int t = lane < 21 ? lane : 20; ei = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15); ej = t - ei * (ei + 1) / 2; }
     const int base = D::NFRIC + e.nlim;
     cdiag = iscube ? (li < 3 ? m.cube_mass : m.cube_inertia[li < 3 ? 0 : li - 3]) : T(0);
     // rows of this lane
@@ -320,19 +342,20 @@ template <class S, typename T, class E> struct WarpSolver {
       Dr[EA] = e.con_D[cc]; Dr[EA + 1] = Dr[EA];
       ar[EA] = e.efc_aref[rp]; ar[EA + 1] = e.efc_aref[rp + 1];
     }
-#pragma unroll
-    for (int k = 0; k < 6; k++) Jr[k] = iscon ? e.Jq[cc][cb][k] : T(0);
     evals = 0;
     qs = isdof ? e.qfrc_smooth[dofi] : T(0);
     // ---- smooth acceleration: factor M (every block), qacc_smooth = M^{-1} qfrc_smooth
-    sfor<0, BS>([&](auto J) {
-      constexpr int j = decltype(J)::value;
-      const T mv = e.M[isarm ? dofi : 0][isarm ? b0 + (j < bn ? j : 0) : 0];
-      row[j] = isarm ? (j < bn ? mv : T(0)) : (j == li ? (iscube ? cdiag : T(1)) : T(0));
-    });
     dinv = 1; hd_cached = 0;
-    factor_blocks();
-    store_rows(isdof);
+    {
+      T row[BS];
+      sfor<0, BS>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const T mv = e.M[isarm ? dofi : 0][isarm ? b0 + (j < bn ? j : 0) : 0];
+        row[j] = isarm ? (j < bn ? mv : T(0)) : (j == li ? (iscube ? cdiag : T(1)) : T(0));
+      });
+      factor_blocks(row);
+      store_rows<BS>(row, isdof);
+    }
     { const T x = solve(qs); as = isdof ? x : T(0); }   // every lane takes part in the shuffles
     if (isdof) e.qacc_smooth[lane] = as;
     // ---- warm start: the previous qacc if it is cheaper than the unconstrained acceleration (rolled: one code site)
