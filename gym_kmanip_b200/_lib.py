@@ -17,7 +17,7 @@ EXPORTS = [
     "km_last_error", "km_version", "km_measure_fma_peak", "km_create", "km_destroy", "km_nq", "km_nv", "km_nu", "km_nmocap", "km_obs_dim",
     "km_act_dim", "km_state_dim", "km_max_contacts", "km_num_envs", "km_dtype", "km_configure", "km_launch_count",
     "km_launch_config", "km_reset", "km_step", "km_get_state", "km_set_state", "km_state_ptr", "km_contacts",
-    "km_solver_stats", "km_debug_phase_clocks", "km_site_poses", "km_n_arm", "km_reset_host", "km_step_host",
+    "km_solver_stats", "km_episode_stats", "km_set_host_stream", "km_debug_phase_clocks", "km_site_poses", "km_n_arm", "km_reset_host", "km_step_host",
     "km_render", "km_render_host", "km_render_record_floats", "km_get_render_records",
 ]
 
@@ -25,7 +25,9 @@ EXPORTS = [
 class StepOut(C.Structure):
     """km_step_out of include/kmanip_b200.h"""
     _fields_ = [("obs", C.c_void_p), ("final_obs", C.c_void_p), ("reward", C.c_void_p), ("truncated", C.c_void_p),
-                ("terminated", C.c_void_p), ("con_flags", C.c_void_p), ("ncon", C.c_void_p), ("con_geoms", C.c_void_p)]
+                ("terminated", C.c_void_p), ("con_flags", C.c_void_p), ("ncon", C.c_void_p), ("con_geoms", C.c_void_p),
+                ("is_success", C.c_void_p), ("episode_return", C.c_void_p), ("final_return", C.c_void_p), ("sim_time", C.c_void_p),
+                ("step_count", C.c_void_p), ("episode", C.c_void_p)]
 
 
 def build(jobs: int = 8, verbose: bool = False) -> str:
@@ -68,6 +70,8 @@ def load() -> C.CDLL:
     L.km_contacts.argtypes = [vp, vp, vp, vp]
     L.km_solver_stats.argtypes = [vp, vp, vp, vp]
     L.km_debug_phase_clocks.argtypes = [vp, vp]
+    L.km_episode_stats.argtypes = [vp, vp, vp, ip, vp]
+    L.km_set_host_stream.argtypes = [vp, vp]
     L.km_site_poses.argtypes = [vp, vp, vp, vp]
     L.km_n_arm.argtypes = [vp]
     L.km_reset_host.argtypes = [vp, vp, vp, vp]

@@ -17,7 +17,7 @@ SCENE_ID = {"solo_arm": 0, "dual_arm": 1, "torso": 2}
 class BatchSim:
     def __init__(self, env_id: str, num_envs: int, device: int = 0, dtype: str = "float32", seed: int = 0, env0: int = 0,
                  ik_iters: int = K.DEVICE_IK_ITERS, ik_teleport: bool = True, max_episode_steps: int = K.MAX_EPISODE_STEPS,
-                 env_kwargs: Optional[dict] = None, ik_mode: int = 0):
+                 env_kwargs: Optional[dict] = None, ik_mode: int = 0, n_sub_steps: int = 0):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("gym_kmanip_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -29,11 +29,16 @@ class BatchSim:
         self.flat = mjcf.load_flat(self.scene)
         self.pm = flatmodel.PackedModel(self.flat)
         self.task = flatmodel.make_task(self.flat, self.kw, ik_iters=ik_iters, ik_teleport=ik_teleport,
-                                        max_episode_steps=max_episode_steps, ik_mode=ik_mode)
+                                        max_episode_steps=max_episode_steps, ik_mode=ik_mode, n_sub_steps=n_sub_steps)
         self.n = int(num_envs)
         self.device_index = int(device)
         self.device = torch.device("cuda", self.device_index)
-        self.tdtype = torch.float32 if dtype in ("float32", 32, torch.float32) else torch.float64
+        if dtype in ("float32", 32, torch.float32):
+            self.tdtype = torch.float32
+        elif dtype in ("float64", 64, torch.float64):
+            self.tdtype = torch.float64
+        else:
+            raise ValueError(f"dtype must be 'float32' or 'float64', got {dtype!r}")
         h = C.c_void_p()
         _lib.check(self.L.km_create(self.pm.ref(), C.byref(self.task), SCENE_ID[self.scene], self.n, self.device_index,
                                     32 if self.tdtype == torch.float32 else 64, seed, env0, C.byref(h)))
@@ -52,11 +57,23 @@ class BatchSim:
         self.con_flags = torch.zeros(self.n, dtype=torch.int32, **kw)
         self.ncon = torch.zeros(self.n, dtype=torch.int32, **kw)
         self.con_geoms = torch.full((self.n, 2 * self.max_contacts), -1, dtype=torch.int32, **kw)
+        # per-step `info` arrays (reference env_base.py:243-250), written by the step kernel itself
+        self.is_success = torch.zeros(self.n, dtype=torch.uint8, **kw)
+        self.episode_return = torch.zeros(self.n, dtype=self.tdtype, **kw)
+        self.final_return = torch.zeros(self.n, dtype=self.tdtype, **kw)
+        self.sim_time = torch.zeros(self.n, dtype=self.tdtype, **kw)
+        self.step_count = torch.zeros(self.n, dtype=torch.int32, **kw)
+        self.episode = torch.zeros(self.n, dtype=torch.int32, **kw)
+        self._out_min = _lib.StepOut(self.obs.data_ptr(), self.final_obs.data_ptr(), self.reward.data_ptr(),
+                                     self.truncated.data_ptr(), None, None, None, None, None, None, None, None, None, None)
+        self._bind_outputs()
+
+    def _bind_outputs(self):
         self._out = _lib.StepOut(self.obs.data_ptr(), self.final_obs.data_ptr(), self.reward.data_ptr(),
                                  self.truncated.data_ptr(), self.terminated.data_ptr(), self.con_flags.data_ptr(),
-                                 self.ncon.data_ptr(), self.con_geoms.data_ptr())
-        self._out_min = _lib.StepOut(self.obs.data_ptr(), self.final_obs.data_ptr(), self.reward.data_ptr(),
-                                     self.truncated.data_ptr(), None, None, None, None)
+                                 self.ncon.data_ptr(), self.con_geoms.data_ptr(), self.is_success.data_ptr(),
+                                 self.episode_return.data_ptr(), self.final_return.data_ptr(), self.sim_time.data_ptr(),
+                                 self.step_count.data_ptr(), self.episode.data_ptr())
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -92,11 +109,15 @@ class BatchSim:
         t = self.torch
         mp = None
         if mask is not None:
-            self._mask = mask.to(device=self.device, dtype=t.uint8).contiguous()
+            self._mask = t.as_tensor(mask).to(device=self.device, dtype=t.uint8).contiguous()
+            if self._mask.numel() != self.n:
+                raise ValueError(f"reset mask must have num_envs = {self.n} entries, got {self._mask.numel()}")
             mp = self._mask.data_ptr()
         xp = None
         if cube_xyz is not None:
-            self._xyz = t.as_tensor(cube_xyz, device=self.device).to(self.tdtype).contiguous().view(self.n, 3)
+            self._xyz = t.as_tensor(cube_xyz, device=self.device).to(self.tdtype).contiguous()
+            if self._xyz.numel() != 3 * self.n:
+                raise ValueError(f"cube_xyz must be [num_envs = {self.n}, 3]")
             xp = self._xyz.data_ptr()
         _lib.check(self.L.km_reset(self.h, mp, xp, self.obs.data_ptr(), self._stream()))
         return self.obs
@@ -104,9 +125,10 @@ class BatchSim:
     def step(self, action, autoreset: bool = True, contacts: bool = True):
         """One env step of every env.  action: float32 CUDA tensor [n, act_dim]."""
         t = self.torch
-        if action.dtype != t.float32 or not action.is_cuda or not action.is_contiguous() or action.numel() != self.n * self.act_dim:
-            action = action.to(device=self.device, dtype=t.float32).contiguous()
-            assert action.numel() == self.n * self.act_dim, "action must be [num_envs, act_dim]"
+        if action.dtype != t.float32 or action.device != self.device or not action.is_contiguous():
+            action = action.to(device=self.device, dtype=t.float32).contiguous()   # (also moves tensors of another GPU)
+        if action.numel() != self.n * self.act_dim:
+            raise ValueError(f"action must be [num_envs = {self.n}, act_dim = {self.act_dim}]")
         self._act = action
         _lib.check(self.L.km_step(self.h, action.data_ptr(), C.byref(self._out if contacts else self._out_min), int(autoreset),
                                   self._stream()))
@@ -116,6 +138,7 @@ class BatchSim:
         """The reference-facing call with HOST buffers (numpy or pinned torch tensors): copies inside."""
         def ptr(x):
             return x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr()
+        self.L.km_set_host_stream(self.h, self._stream())   # same stream as the device-pointer calls: ordered with them
         _lib.check(self.L.km_step_host(self.h, ptr(action_host), ptr(obs_host), ptr(reward_host), ptr(truncated_host),
                                        int(autoreset)))
 
@@ -123,6 +146,7 @@ class BatchSim:
         """km_reset_host: reset with HOST buffers (numpy or pinned torch tensors; any may be None)."""
         def ptr(x):
             return None if x is None else (x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr())
+        self.L.km_set_host_stream(self.h, self._stream())
         _lib.check(self.L.km_reset_host(self.h, ptr(mask_host), ptr(cube_xyz_host), ptr(obs_host)))
 
     # ------------------------------------------------------------------ state access (teacher forcing, physics shim)
@@ -192,6 +216,7 @@ class BatchSim:
         """km_render_host: the same with a HOST image buffer [n, h, w, 3] uint8 (copy inside)."""
         from . import render as R
         cam = K.CAMERAS[cam] if isinstance(cam, str) else cam
+        self.L.km_set_host_stream(self.h, self._stream())
         _lib.check(self.L.km_render_host(self.h, C.byref(R.camera_struct(self.flat, cam.name, cam.w, cam.h)),
                                          C.byref(R.visual_struct(self.flat)), out.ctypes.data))
         return out
@@ -203,6 +228,14 @@ class BatchSim:
         out = t.empty(self.n, nf, dtype=t.float32, device=self.device)
         _lib.check(self.L.km_get_render_records(self.h, out.data_ptr(), self._stream()))
         return out
+
+    def episode_stats(self, reset: bool = False):
+        """Rollout totals accumulated by the step kernel: float64 CUDA tensor [sum of rewards, env steps, finished episodes,
+        success steps] since the last reset of the totals (km_episode_stats); reset=True zeroes them afterwards."""
+        t = self.torch
+        tot = t.empty(4, dtype=t.float64, device=self.device)
+        _lib.check(self.L.km_episode_stats(self.h, tot.data_ptr(), None, int(reset), self._stream()))
+        return tot
 
     def solver_stats(self):
         t = self.torch

@@ -32,6 +32,9 @@ struct km_sim {
   void* d_state;
   int *d_step, *d_episode, *d_niter, *d_ls;
   unsigned* d_clk;   // caller-owned buffer of km_debug_phase_clocks (debug builds)
+  void* d_ep_return;  // running return of every env (dtype of the handle)
+  double* d_totals;   // rollout totals {sum reward, env steps, finished episodes, success steps}
+  cudaStream_t host_stream;   // stream of the *_host entry points
   // staging for the host-buffer entry points
   float* d_act;
   void *d_obs, *d_reward, *d_xyz;
@@ -117,6 +120,7 @@ static int configure(km_sim* h, int G, int epb) {
   if ((G != 16 && G != 32) || G < h->vt.nlanes_min) return fail(KM_ERR_ARG, "lanes_per_env must be 1, 16 or 32 and (for 16 / 32) at least the number of dofs");
   int dev_smem = 0;
   KM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  dev_smem -= (int)km::KM_SMEM_STATIC;   // the kernels' static shared memory (CTA totals) comes out of the same budget
   const size_t model_b = (h->vt.model_bytes + 15) / 16 * 16;
   const int fit = (int)(((size_t)dev_smem - model_b) / h->vt.env_bytes);
   const int cap = fit * G > h->vt.max_threads ? h->vt.max_threads / G : fit;
@@ -149,6 +153,7 @@ static KmArgs base_args(km_sim* h, void* stream) {
   std::memset(&a, 0, sizeof(a));
   a.model = h->d_model; a.state = h->d_state; a.step = h->d_step; a.episode = h->d_episode;
   a.niter = h->d_niter; a.ls = h->d_ls; a.clk = h->d_clk;
+  a.ep_return = h->d_ep_return; a.totals = h->d_totals;
   a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid; a.lpw = h->lpw > 0 ? h->lpw : 32; a.tpl_small_regs = h->tpl_ctas > 1;
   a.stream = (cudaStream_t)stream;
   return a;
@@ -245,12 +250,16 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   KM_ALLOC(h->d_xyz, n * 3 * sb);
   KM_ALLOC(h->d_trunc, n);
   KM_ALLOC(h->d_mask, n);
+  KM_ALLOC(h->d_ep_return, n * sb);
+  KM_ALLOC(h->d_totals, 4 * sizeof(double));
 #undef KM_ALLOC
   if ((e = cudaMemcpy(h->d_model, host_model.data(), h->vt.model_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemset(h->d_state, 0, n * h->vt.state_dim * sb)) != cudaSuccess ||
       (e = cudaMemset(h->d_step, 0, n * sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->d_episode, 0xff, n * sizeof(int))) != cudaSuccess ||   // -1: the first reset starts episode 0
       (e = cudaMemset(h->d_niter, 0, n * sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(h->d_ep_return, 0, n * sb)) != cudaSuccess ||
+      (e = cudaMemset(h->d_totals, 0, 4 * sizeof(double))) != cudaSuccess ||
       (e = cudaMemset(h->d_ls, 0, n * sizeof(int))) != cudaSuccess) {
     km_destroy(h);
     return cuda_fail(e, "km_create: initialisation");
@@ -277,7 +286,7 @@ void km_destroy(km_handle h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   void* ptrs[] = {h->d_model, h->d_state, h->d_step, h->d_episode, h->d_niter, h->d_ls, h->d_act, h->d_obs, h->d_reward,
-                  h->d_xyz, h->d_trunc, h->d_mask, h->d_recs, h->d_rgb};
+                  h->d_xyz, h->d_trunc, h->d_mask, h->d_recs, h->d_rgb, h->d_ep_return, h->d_totals};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -330,6 +339,8 @@ int km_step(km_handle h, const float* action_dev, const km_step_out* out, int au
   if (out) {
     a.obs = out->obs; a.final_obs = out->final_obs; a.reward = out->reward; a.trunc = out->truncated; a.term = out->terminated;
     a.con_flags = out->con_flags; a.ncon = out->ncon; a.con_geoms = out->con_geoms;
+    a.is_success = out->is_success; a.episode_return = out->episode_return; a.final_return = out->final_return;
+    a.sim_time = out->sim_time; a.step_out = out->step_count; a.episode_out = out->episode;
   }
   KM_CUDA(h->vt.step(a));
   h->launches++;
@@ -386,6 +397,22 @@ int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream
   cudaStream_t s = (cudaStream_t)stream;
   if (niter_dev) KM_CUDA(cudaMemcpyAsync(niter_dev, h->d_niter, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
   if (ls_evals_dev) KM_CUDA(cudaMemcpyAsync(ls_evals_dev, h->d_ls, (size_t)h->n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return KM_OK;
+}
+
+int km_episode_stats(km_handle h, double* totals_dev, void* episode_return_dev, int reset, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (totals_dev) KM_CUDA(cudaMemcpyAsync(totals_dev, h->d_totals, 4 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  if (episode_return_dev) KM_CUDA(cudaMemcpyAsync(episode_return_dev, h->d_ep_return, (size_t)h->n * h->vt.scalar_bytes, cudaMemcpyDeviceToDevice, s));
+  if (reset) KM_CUDA(cudaMemsetAsync(h->d_totals, 0, 4 * sizeof(double), s));
+  return KM_OK;
+}
+
+int km_set_host_stream(km_handle h, void* stream) {
+  if (!h) return fail(KM_ERR_ARG, "null handle");
+  h->host_stream = (cudaStream_t)stream;
   return KM_OK;
 }
 
@@ -448,7 +475,8 @@ int km_render(km_handle h, const km_camera* cam, const km_visual* vis, unsigned 
 }
 
 int km_render_host(km_handle h, const km_camera* cam, const km_visual* vis, unsigned char* rgb_host) {
-  if (!h || !cam || !rgb_host) return fail(KM_ERR_ARG, "km_render_host: null argument");
+  if (!h || !cam || !vis || !rgb_host) return fail(KM_ERR_ARG, "km_render_host: null argument");
+  if (cam->width < 1 || cam->height < 1 || cam->width > 16384 || cam->height > 16384) return fail(KM_ERR_ARG, "km_render_host: bad camera size");
   DeviceGuard guard(h->device);
   const size_t bytes = (size_t)h->n * cam->width * cam->height * 3;
   if (bytes > h->rgb_bytes) {
@@ -457,10 +485,10 @@ int km_render_host(km_handle h, const km_camera* cam, const km_visual* vis, unsi
     KM_CUDA(cudaMalloc((void**)&h->d_rgb, bytes));
     h->rgb_bytes = bytes;
   }
-  int rc = km_render(h, cam, vis, h->d_rgb, nullptr);
+  int rc = km_render(h, cam, vis, h->d_rgb, (void*)h->host_stream);
   if (rc != KM_OK) return rc;
-  KM_CUDA(cudaMemcpyAsync(rgb_host, h->d_rgb, bytes, cudaMemcpyDeviceToHost, 0));
-  KM_CUDA(cudaStreamSynchronize(0));
+  KM_CUDA(cudaMemcpyAsync(rgb_host, h->d_rgb, bytes, cudaMemcpyDeviceToHost, h->host_stream));
+  KM_CUDA(cudaStreamSynchronize(h->host_stream));
   return KM_OK;
 }
 
@@ -477,12 +505,13 @@ int km_reset_host(km_handle h, const unsigned char* mask, const void* cube_xyz, 
   if (!h) return fail(KM_ERR_ARG, "null handle");
   DeviceGuard guard(h->device);
   const size_t n = (size_t)h->n, sb = h->vt.scalar_bytes;
-  if (mask) KM_CUDA(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, 0));
-  if (cube_xyz) KM_CUDA(cudaMemcpyAsync(h->d_xyz, cube_xyz, n * 3 * sb, cudaMemcpyHostToDevice, 0));
-  int rc = km_reset(h, mask ? h->d_mask : nullptr, cube_xyz ? h->d_xyz : nullptr, obs ? h->d_obs : nullptr, nullptr);
+  cudaStream_t hs = h->host_stream;
+  if (mask) KM_CUDA(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, hs));
+  if (cube_xyz) KM_CUDA(cudaMemcpyAsync(h->d_xyz, cube_xyz, n * 3 * sb, cudaMemcpyHostToDevice, hs));
+  int rc = km_reset(h, mask ? h->d_mask : nullptr, cube_xyz ? h->d_xyz : nullptr, obs ? h->d_obs : nullptr, (void*)hs);
   if (rc != KM_OK) return rc;
-  if (obs) KM_CUDA(cudaMemcpyAsync(obs, h->d_obs, n * h->vt.obs_dim * sb, cudaMemcpyDeviceToHost, 0));
-  KM_CUDA(cudaStreamSynchronize(0));
+  if (obs) KM_CUDA(cudaMemcpyAsync(obs, h->d_obs, n * h->vt.obs_dim * sb, cudaMemcpyDeviceToHost, hs));
+  KM_CUDA(cudaStreamSynchronize(hs));
   return KM_OK;
 }
 
@@ -490,17 +519,18 @@ int km_step_host(km_handle h, const float* action, void* obs, void* reward, unsi
   if (!h || !action) return fail(KM_ERR_ARG, "km_step_host: null handle or action");
   DeviceGuard guard(h->device);
   const size_t n = (size_t)h->n, sb = h->vt.scalar_bytes;
+  cudaStream_t hs = h->host_stream;
   int act_dim = km_act_dim(h);
-  KM_CUDA(cudaMemcpyAsync(h->d_act, action, n * act_dim * sizeof(float), cudaMemcpyHostToDevice, 0));
+  KM_CUDA(cudaMemcpyAsync(h->d_act, action, n * act_dim * sizeof(float), cudaMemcpyHostToDevice, hs));
   km_step_out o;
   std::memset(&o, 0, sizeof(o));
   o.obs = obs ? h->d_obs : nullptr; o.reward = reward ? h->d_reward : nullptr; o.truncated = truncated ? h->d_trunc : nullptr;
-  int rc = km_step(h, h->d_act, &o, autoreset, nullptr);
+  int rc = km_step(h, h->d_act, &o, autoreset, (void*)hs);
   if (rc != KM_OK) return rc;
-  if (obs) KM_CUDA(cudaMemcpyAsync(obs, h->d_obs, n * h->vt.obs_dim * sb, cudaMemcpyDeviceToHost, 0));
-  if (reward) KM_CUDA(cudaMemcpyAsync(reward, h->d_reward, n * sb, cudaMemcpyDeviceToHost, 0));
-  if (truncated) KM_CUDA(cudaMemcpyAsync(truncated, h->d_trunc, n, cudaMemcpyDeviceToHost, 0));
-  KM_CUDA(cudaStreamSynchronize(0));
+  if (obs) KM_CUDA(cudaMemcpyAsync(obs, h->d_obs, n * h->vt.obs_dim * sb, cudaMemcpyDeviceToHost, hs));
+  if (reward) KM_CUDA(cudaMemcpyAsync(reward, h->d_reward, n * sb, cudaMemcpyDeviceToHost, hs));
+  if (truncated) KM_CUDA(cudaMemcpyAsync(truncated, h->d_trunc, n, cudaMemcpyDeviceToHost, hs));
+  KM_CUDA(cudaStreamSynchronize(hs));
   return KM_OK;
 }
 

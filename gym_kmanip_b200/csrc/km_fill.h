@@ -206,7 +206,7 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
   for (int i = 0; i < 3; i++) m.grav[i] = (T)fm->gravity[i];
   m.tol = (T)fm->tolerance; m.ls_tol = (T)fm->ls_tolerance; m.meaninertia = (T)fm->meaninertia; m.impratio = (T)fm->impratio;
   m.iterations = fm->iterations; m.ls_iterations = fm->ls_iterations;
-  m.nsub = (int)std::lround(0.02 / fm->timestep);   // CONTROL_TIMESTEP, reference __init__.py:30
+  m.nsub = tk->n_sub_steps > 0 ? tk->n_sub_steps : (int)std::lround(0.02 / fm->timestep);   // CONTROL_TIMESTEP, reference __init__.py:30
   // ---- task
   m.act_dim = tk->act_dim; m.act_mode = tk->act_mode; m.n_arm = tk->n_arm;
   KM_FILL_CHECK(tk->n_arm <= D::NARM && tk->cube_body == cube_b && tk->cube_qposadr == D::NVA, "task does not match the scene");

@@ -30,6 +30,10 @@ struct KmArgs {
   int* niter;
   int* ls;
   unsigned* clk;   // debug build (KM_PHASE_CLOCKS): per-env phase cycles of the step
+  // episode bookkeeping: persistent running return [n], optional per-step info outputs, rollout totals double[4]
+  void* ep_return; void* episode_return; void* final_return; void* sim_time;
+  unsigned char* is_success; int* step_out; int* episode_out;
+  double* totals;
   const unsigned char* mask;
   const void* cube_xyz;
   void* site_pos;
@@ -59,13 +63,16 @@ struct KmVtable {
 
 #if defined(__CUDACC__)
 
+// opt-in shared memory of one CTA on sm_100a (227 KB) minus the kernels' few bytes of static shared memory (CTA totals)
+constexpr size_t KM_SMEM_STATIC = 64;
+constexpr size_t KM_SMEM_OPTIN = 232448 - KM_SMEM_STATIC;
 template <class S, typename T> constexpr size_t model_smem() { return (sizeof(Model<S, T>) + 15) / 16 * 16; }
 template <class S, typename T> constexpr size_t env_smem() { return (sizeof(Env<S, T>) + 15) / 16 * 16; }
 template <class S, typename T> size_t smem_bytes(int epb) { return model_smem<S, T>() + (size_t)epb * env_smem<S, T>(); }
 // most envs one CTA can hold in the 227 KB of opt-in shared memory (one warp each at G = 32), and the thread bound
 // the kernels are compiled for (it caps registers so that such a CTA is resident: 65536 / threads)
 template <class S, typename T> constexpr int max_epb() {
-  return (int)((232448 - model_smem<S, T>()) / env_smem<S, T>()) > 32 ? 32 : (int)((232448 - model_smem<S, T>()) / env_smem<S, T>());
+  return (int)((KM_SMEM_OPTIN - model_smem<S, T>()) / env_smem<S, T>()) > 32 ? 32 : (int)((KM_SMEM_OPTIN - model_smem<S, T>()) / env_smem<S, T>());
 }
 template <class S, typename T> constexpr int max_threads() { return 32 * max_epb<S, T>(); }
 
@@ -103,6 +110,12 @@ template <class S, typename T, int G, class E_> __device__ __forceinline__ void 
   if (g.lane == 0) { a.step[env] = e.step; a.episode[env] = e.episode; }
 }
 
+// one add per CTA to the handle's rollout totals (after every env of the CTA has stepped)
+__device__ __forceinline__ void flush_totals(const KmArgs& a, const double* cta_totals) {
+  __syncthreads();
+  if (a.totals && threadIdx.x < 4 && cta_totals[threadIdx.x] != 0.0) atomicAdd(a.totals + threadIdx.x, cta_totals[threadIdx.x]);
+}
+
 template <class S, typename T, int G> __global__ void __launch_bounds__(max_threads<S, T>()) k_env_step(KmArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const Model<S, T>& m = stage_model<S, T>(smem, a.model);
@@ -110,7 +123,12 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
   const int slot = threadIdx.x / G;
   Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
   init_env<S, T, G>(e, m, g);
-  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON, a.clk};
+  __shared__ double cta_totals[4];
+  if (threadIdx.x < 4) cta_totals[threadIdx.x] = 0;
+  __syncthreads();
+  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON, a.clk,
+                  (T*)a.ep_return, (T*)a.episode_return, (T*)a.final_return, (T*)a.sim_time, a.is_success, a.step_out, a.episode_out,
+                  a.totals ? cta_totals : nullptr};
   // every warp walks the same number of tiles so that the groups sharing a warp can reconverge
   for (long tile = (long)blockIdx.x * a.epb; tile < a.n; tile += (long)gridDim.x * a.epb) {
     const long env = tile + slot;
@@ -121,7 +139,8 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
     }
     // env slots past the end of the batch shadow the tile's first env (the CTA marches in phase) and store nothing
     const long envc = valid ? env : tile;
-    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr};
+    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     load_state<S, T, G>(e, a, envc, g);
     env_step<S, T, G>(e, m, g, a.act + envc * m.act_dim, valid ? o : none, envc, a.autoreset, a.seed, a.env0);
     if (valid) {
@@ -133,6 +152,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
     }
     g.sync();
   }
+  flush_totals(a, cta_totals);
 }
 
 // Thread-per-env mapping (G = 1): every thread owns one env; its working set is one contiguous record in shared
@@ -143,7 +163,7 @@ template <class S, typename T> struct Tpe {
   static constexpr size_t words = (sizeof(E) + unit - 1) / unit;
   static constexpr size_t stride = (words | 1) * unit;                 // odd number of bank units per record
   static constexpr int max_envs() {
-    const int fit = (int)((232448 - model_smem<S, T>()) / stride);
+    const int fit = (int)((KM_SMEM_OPTIN - model_smem<S, T>()) / stride);
     return fit > 128 ? 128 : fit;
   }
   static constexpr int threads() { return (max_envs() + 31) / 32 * 32; }
@@ -158,17 +178,23 @@ template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __lau
   const Model<S, T>& m = stage_model<S, T>(smem, a.model);
   Grp<1> g;
   g.lane = 0; g.mask = 1u; g.wmask = 1u;
-  if (!LOCAL && (int)threadIdx.x >= a.epb) return;          // a CTA may hold fewer envs than its rounded-up warp
   E e_local;
-  E& e = LOCAL ? e_local : *(E*)(smem + model_smem<S, T>() + (size_t)threadIdx.x * Tpe<S, T>::stride);
-  init_env<S, T, 1>(e, m, g);
-  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON, a.clk};
+  const bool has_slot = LOCAL || (int)threadIdx.x < a.epb;   // shared-memory records: a CTA may hold fewer envs than threads
+  E& e = LOCAL ? e_local : *(E*)(smem + model_smem<S, T>() + (size_t)(has_slot ? threadIdx.x : 0) * Tpe<S, T>::stride);
+  if (has_slot) init_env<S, T, 1>(e, m, g);
+  __shared__ double cta_totals[4];
+  if (threadIdx.x < 4) cta_totals[threadIdx.x] = 0;
+  __syncthreads();
+  StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON, a.clk,
+                  (T*)a.ep_return, (T*)a.episode_return, (T*)a.final_return, (T*)a.sim_time, a.is_success, a.step_out, a.episode_out,
+                  a.totals ? cta_totals : nullptr};
   if (LOCAL) {
     // Every thread of the CTA walks the same number of tiles, and the warps of the CTA are kept in the same phase of
     // the sub-step by CTA barriers (the sub-step body is far larger than the instruction cache); threads past the end
     // of the batch shadow the tile's first env and store nothing.
     g.wmask = 0xffffffffu;
-    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr};
+    const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const long tiles = ((long)a.n + a.epb - 1) / a.epb;
     for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       // envs of the tile are dealt to the warps lpw at a time: with few envs per SM every scheduler still gets a
@@ -185,9 +211,11 @@ template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __lau
         if (a.ls) a.ls[env] = e.ls_evals;
       }
     }
+    flush_totals(a, cta_totals);
     return;
   }
-  for (long env = (long)blockIdx.x * a.epb + threadIdx.x; env < a.n; env += (long)gridDim.x * a.epb) {
+  // (a CTA may hold fewer envs than its rounded-up warp: the surplus threads step nothing)
+  for (long env = (long)blockIdx.x * a.epb + threadIdx.x; has_slot && env < a.n; env += (long)gridDim.x * a.epb) {
     load_state<S, T, 1>(e, a, env, g);
 #ifdef KM_TPE_DEBUG
     const long long t0 = clock64();
@@ -201,6 +229,7 @@ template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __lau
     if (a.ls) a.ls[env] = (int)((clock64() - t0) >> 10);   // debug build: kilo-cycles of this thread's env step
 #endif
   }
+  flush_totals(a, cta_totals);
 }
 
 template <class S, typename T, int G> __global__ void __launch_bounds__(max_threads<S, T>()) k_reset(KmArgs a) {
@@ -211,7 +240,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
   Env<S, T>& e = *(Env<S, T>*)(smem + model_smem<S, T>() + (size_t)slot * env_smem<S, T>());
   for (long env = (long)blockIdx.x * a.epb + slot; env < a.n; env += (long)gridDim.x * a.epb) {
     if (a.mask && !a.mask[env]) continue;
-    if (g.lane == 0) { e.episode = a.episode[env] + 1; }
+    if (g.lane == 0) { e.episode = a.episode[env] + 1; if (a.ep_return) ((T*)a.ep_return)[env] = 0; }
     g.sync();
     reset_state<S, T, G>(e, m, g, a.seed, a.env0 + (unsigned long long)env, a.cube_xyz ? (const T*)a.cube_xyz + 3 * env : (const T*)0);
     observation<S, T, G>(e, m, g);
@@ -320,9 +349,9 @@ template <class S, typename T> struct Launch {
     cudaError_t err;
     if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
     if ((err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(k_env_step<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(k_reset<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(k_contacts<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_env_step<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)KM_SMEM_STATIC)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_reset<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)KM_SMEM_STATIC)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(k_contacts<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)KM_SMEM_STATIC)) != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, smem_bytes<S, T>(epb));
   }
   static cudaError_t prepare(int G, int epb, int* ctas) {
@@ -332,7 +361,7 @@ template <class S, typename T> struct Launch {
       int dev = 0, optin = 0;
       if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
       if ((err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return err;
-      if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin)) != cudaSuccess) return err;
+      if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)KM_SMEM_STATIC)) != cudaSuccess) return err;
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, false>, (epb + 31) / 32 * 32, Tpe<S, T>::smem(epb));
     }
     if (G == 2) {

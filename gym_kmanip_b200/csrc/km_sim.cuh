@@ -1279,7 +1279,20 @@ template <typename T> struct StepOut {
   T* obs; T* final_obs; T* reward; unsigned char* truncated; unsigned char* terminated;
   int* con_flags; int* ncon; int* con_geoms; int con_cap;
   unsigned* clk;   // debug build (KM_PHASE_CLOCKS): [n][16] cycles per phase of this env step
+  // episode bookkeeping (reference env_base.py:243-250 `info`, batched): running return of every env (persistent),
+  // per-step info arrays, and the CTA's accumulators of the rollout totals {sum reward, env steps, finished episodes,
+  // success steps} that the kernel adds to the handle's totals once per CTA
+  T* ep_return; T* episode_return; T* final_return; T* sim_time; unsigned char* is_success; int* step_out; int* episode_out;
+  double* cta_totals;
 };
+// adds to one of a CTA's accumulators (shared memory on the device; plain memory in the host build of the tests)
+KM_HD void km_accumulate(double* dst, double v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(dst, v);
+#else
+  *dst += v;
+#endif
+}
 
 // One env step on the working set already holding the env's state.
 KM_TPL KM_FN void env_step(KM_ARGS, const float* act, const StepOut<T>& o, long env, int autoreset, uint64_t seed,
@@ -1321,6 +1334,25 @@ KM_TPL KM_FN void env_step(KM_ARGS, const float* act, const StepOut<T>& o, long 
   if (g.lane == 0) {
     if (o.truncated) o.truncated[env] = trunc ? 1 : 0;
     if (o.terminated) o.terminated[env] = 0;   // the reference never terminates
+    // info of this step (env_base.py:243-250): step index inside the episode, episode index, simulation time,
+    // is_success = reward > REWARD_SUCCESS_THRESHOLD (2.0, __init__.py:204), the running and the finished return
+    const bool success = r > T(2);
+    if (o.is_success) o.is_success[env] = success ? 1 : 0;
+    if (o.step_out) o.step_out[env] = e.step;
+    if (o.episode_out) o.episode_out[env] = e.episode;
+    if (o.sim_time) o.sim_time[env] = e.time;
+    if (o.ep_return) {
+      const T ret = o.ep_return[env] + r;
+      if (o.episode_return) o.episode_return[env] = ret;
+      if (o.final_return) o.final_return[env] = trunc ? ret : T(0);
+      o.ep_return[env] = (autoreset && trunc) ? T(0) : ret;
+    }
+    if (o.cta_totals) {
+      km_accumulate(o.cta_totals + 0, (double)r);
+      km_accumulate(o.cta_totals + 1, 1.0);
+      km_accumulate(o.cta_totals + 2, trunc ? 1.0 : 0.0);
+      km_accumulate(o.cta_totals + 3, success ? 1.0 : 0.0);
+    }
   }
   if (autoreset && trunc) {
     // same-step autoreset: final_obs keeps the last observation of the finished episode

@@ -48,7 +48,7 @@ class CTask(C.Structure):
         ("arm_site", C.c_int * MAXARM), ("arm_eebody", C.c_int * MAXARM), ("arm_mocap", C.c_int * MAXARM),
         ("off_pos", C.c_int * MAXARM), ("off_orn", C.c_int * MAXARM), ("off_grip", C.c_int * MAXARM), ("off_q", C.c_int * MAXARM),
         ("cube_body", C.c_int), ("cube_qposadr", C.c_int), ("ik_iters", C.c_int), ("ik_teleport", C.c_int),
-        ("max_episode_steps", C.c_int), ("ik_mode", C.c_int),
+        ("max_episode_steps", C.c_int), ("ik_mode", C.c_int), ("n_sub_steps", C.c_int), ("reserved0", C.c_int),
         ("q_home", C.c_double * 32), ("cube_spawn_lo", C.c_double * 3), ("cube_spawn_hi", C.c_double * 3),
     ]
 
@@ -94,7 +94,7 @@ def action_layout(act_list: List[str], n_r: int, n_l: int) -> Dict[str, slice]:
 
 
 def make_task(flat: Dict, env_kwargs: Dict, ik_iters: int = K.DEVICE_IK_ITERS, ik_teleport: bool = True,
-              max_episode_steps: int = K.MAX_EPISODE_STEPS, ik_mode: int = 0) -> CTask:
+              max_episode_steps: int = K.MAX_EPISODE_STEPS, ik_mode: int = 0, n_sub_steps: int = 0) -> CTask:
     """Task struct for one registered env id (kwargs as in constants.ENV_REGISTRY)."""
     act_list = env_kwargs["act_list"]
     t = CTask()
@@ -137,6 +137,7 @@ def make_task(flat: Dict, env_kwargs: Dict, ik_iters: int = K.DEVICE_IK_ITERS, i
     t.ik_teleport = int(ik_teleport)
     t.max_episode_steps = max_episode_steps
     t.ik_mode = int(ik_mode)
+    t.n_sub_steps = int(n_sub_steps)    # 0: the reference's 10 (control timestep 0.02 s / physics timestep 0.002 s)
     for i in range(3):
         t.cube_spawn_lo[i] = float(K.CUBE_SPAWN_RANGE[i, 0])
         t.cube_spawn_hi[i] = float(K.CUBE_SPAWN_RANGE[i, 1])

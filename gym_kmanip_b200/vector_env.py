@@ -21,9 +21,14 @@ from .spaces import Box, Dict as DictSpace
 
 class KManipVectorEnv:
     def __init__(self, env_id: str, num_envs: int, device: int = 0, dtype: str = "float32", seed: int = 0, env0: int = 0,
-                 max_episode_steps: int = K.MAX_EPISODE_STEPS, log_dir: Optional[str] = None, log_env_ids=None, **sim_kwargs):
+                 max_episode_steps: int = K.MAX_EPISODE_STEPS, log_dir: Optional[str] = None, log_env_ids=None,
+                 copy: bool = True, **sim_kwargs):
+        """copy=True (default, what gymnasium's VectorEnv does): reset() / step() return fresh tensors, so an observation
+        kept from one step is not overwritten by the next.  copy=False returns views into the simulator's output buffers
+        (zero extra kernels; the next step overwrites them -- only for loops that consume an observation before stepping)."""
         kw = K.ENV_REGISTRY[env_id]
         self.env_id, self.num_envs = env_id, int(num_envs)
+        self.copy = bool(copy)
         self.sim = BatchSim(env_id, num_envs, device=device, dtype=dtype, seed=seed, env0=env0,
                             max_episode_steps=max_episode_steps, **sim_kwargs)
         self.device = self.sim.device
@@ -50,9 +55,6 @@ class KManipVectorEnv:
             (k, Box(-1, 1, (self.num_envs,) + tuple(sp.shape), sp.dtype)) for k, sp in self.single_action_space.spaces.items()))
         t = self.sim.torch
         self._act = t.zeros(self.num_envs, self.sim.act_dim, dtype=t.float32, device=self.device)
-        self.episode_return = t.zeros(self.num_envs, dtype=t.float64, device=self.device)
-        # running totals of the rollout: sum of rewards, env steps, finished episodes, success steps
-        self.totals = t.zeros(4, dtype=t.float64, device=self.device)
         # episode logger (reference log_h5py.py) fed from device ring buffers; log_env_ids: local env indices (default: env 0)
         self.log = None
         if log_dir is not None:
@@ -64,11 +66,27 @@ class KManipVectorEnv:
 
     # -------------------------------------------------------------------------------- helpers
     def _obs_dict(self, flat, images: bool = True) -> "OrderedDict[str, object]":
+        if self.copy:
+            flat = flat.clone()
         obs = OrderedDict((k, flat[:, sl]) for k, sl in self.obs_layout.items())
         if images:
-            for c in self.cameras:          # images of the stored (post-step, post-autoreset) state; buffers are reused
-                obs[c.log_name] = self.sim.render(c, out=self._images[c.log_name])
+            for c in self.cameras:          # images of the stored (post-step, post-autoreset) state
+                obs[c.log_name] = self.sim.render(c, out=None if self.copy else self._images[c.log_name])
         return obs
+
+    def _out(self, x):
+        return x.clone() if self.copy else x
+
+    @property
+    def episode_return(self):
+        """Running return of every env (accumulated by the step kernel)."""
+        return self.sim.episode_return
+
+    @property
+    def totals(self):
+        """Rollout totals [sum of rewards, env steps, finished episodes, success steps] accumulated by the step kernel
+        (km_episode_stats): a float64 CUDA tensor."""
+        return self.sim.episode_stats()
 
     def flatten_action(self, action):
         """Dict of [n, k] tensors (reference keys) -> the flat [n, act_dim] float32 record; flat tensors pass through."""
@@ -88,33 +106,27 @@ class KManipVectorEnv:
         mask = cube = None
         if options:
             mask, cube = options.get("reset_mask"), options.get("cube_xyz")
-        flat = self.sim.reset(mask=mask, cube_xyz=cube)
-        if mask is None:
-            self.episode_return.zero_()
-        else:
-            self.episode_return.masked_fill_(mask.to(self.device).bool(), 0.0)
+        flat = self.sim.reset(mask=mask, cube_xyz=cube)     # (the reset kernel also zeroes the running returns)
         return self._obs_dict(flat), {}
 
     def step(self, action):
-        t = self.sim.torch
+        """One env step of every env: ONE kernel launch.  Returns (obs, reward, terminated, truncated, info); info holds
+        the batched form of the reference's per-step info (env_base.py:243-250): is_success, episode, step, sim_time, plus
+        final_obs / final_return of the episodes that ended on this step, episode_return, con_flags, ncon."""
         act = self.flatten_action(action)
-        flat, rew, term, trunc = self.sim.step(act, autoreset=True)
+        sim = self.sim
+        flat, rew, term, trunc = sim.step(act, autoreset=True)
         if self.log is not None:
-            self.log.step(act, flat, self.sim.final_obs, trunc)
-        success = rew > K.REWARD_SUCCESS_THRESHOLD                   # env_base.py:249
-        done = trunc.bool()
-        self.episode_return += rew.double()
+            self.log.step(act, flat, sim.final_obs, trunc)
+        o = self._out
+        # flags: bool tensors in copy mode (a conversion is a fresh tensor already); the simulator's uint8 buffers otherwise
+        f = (lambda x: x.bool()) if self.copy else (lambda x: x)
         info: Dict[str, object] = {
-            "is_success": success, "final_obs": self._obs_dict(self.sim.final_obs, images=False),
-            "final_return": t.where(done, self.episode_return, t.zeros_like(self.episode_return)),
-            "con_flags": self.sim.con_flags, "ncon": self.sim.ncon,
+            "is_success": f(sim.is_success), "episode": o(sim.episode), "step": o(sim.step_count), "sim_time": o(sim.sim_time),
+            "final_obs": self._obs_dict(sim.final_obs, images=False), "final_return": o(sim.final_return),
+            "episode_return": o(sim.episode_return), "con_flags": o(sim.con_flags), "ncon": o(sim.ncon),
         }
-        self.totals[0] += rew.sum(dtype=t.float64)
-        self.totals[1] += self.num_envs
-        self.totals[2] += done.sum(dtype=t.float64)
-        self.totals[3] += success.sum(dtype=t.float64)
-        self.episode_return.masked_fill_(done, 0.0)
-        return self._obs_dict(flat), rew, term.bool(), done, info
+        return self._obs_dict(flat), o(rew), f(term), f(trunc), info
 
     @property
     def sim_step_counts(self):

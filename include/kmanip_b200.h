@@ -78,6 +78,9 @@ typedef struct km_task {
   int cube_body, cube_qposadr;
   int ik_iters, ik_teleport, max_episode_steps;
   int ik_mode;                           /* 0: fixed-iteration projected LM (fast path); 1: restated scipy TRF (exact-parity mode) */
+  int n_sub_steps;                       /* physics sub-steps per env step; 0 = round(CONTROL_TIMESTEP / timestep) = 10 (__init__.py:30).
+                                            Tests set 1 to compare single mj_step's (per-sub-step parity) */
+  int reserved0;
   double q_home[32], cube_spawn_lo[3], cube_spawn_hi[3];
 } km_task;
 
@@ -97,6 +100,13 @@ typedef struct km_step_out {
   int* con_flags;            /* [n] bit0 cube-table, bit1 right finger pads, bit2 left finger pads */
   int* ncon;                 /* [n] */
   int* con_geoms;            /* [n][2*km_max_contacts] (geom1, geom2) per contact, -1 padded */
+  /* the per-step `info` of reference env_base.py:243-250, as arrays: */
+  unsigned char* is_success; /* [n] reward > REWARD_SUCCESS_THRESHOLD (2.0) */
+  void* episode_return;      /* [n] return of the running episode including this step (dtype of the handle) */
+  void* final_return;        /* [n] return of the episode this step finished (truncated), else 0 */
+  void* sim_time;            /* [n] simulation time after the step (before an autoreset) */
+  int* step_count;           /* [n] step index inside the episode after this step (max_episode_steps where truncated) */
+  int* episode;              /* [n] index of the episode this step belongs to */
 } km_step_out;
 
 const char* km_last_error(void);
@@ -187,6 +197,16 @@ int km_get_render_records(km_handle h, float* recs_dev, void* stream);
 
 /* Diagnostics of the most recent step's last sub-step: [n] Newton iterations, [n] line-search evaluations (cumulative). */
 int km_solver_stats(km_handle h, int* niter_dev, int* ls_evals_dev, void* stream);
+/* Rollout statistics accumulated by the step kernel itself (no extra launches): totals_dev[4] = {sum of rewards, env
+   steps, finished (truncated) episodes, success steps} over every km_step since the last reset of the totals, and/or the
+   running return of every env (episode_return_dev [n], dtype of the handle).  Either pointer may be NULL.  reset != 0
+   zeroes the totals after they were copied.  The sums are formed with floating-point atomics (one per CTA): their last
+   bits depend on the order in which CTAs finish. */
+int km_episode_stats(km_handle h, double* totals_dev, void* episode_return_dev, int reset, void* stream);
+/* Stream used by the *_host entry points (default: the legacy default stream).  Callers that mix the host-buffer calls
+   with stream-ordered device-pointer calls pass the same stream to both. */
+int km_set_host_stream(km_handle h, void* stream);
+
 /* Profiling aid: after this call every km_step also writes [n][16] uint32 cycle counts per phase of the env step
    (position stage, velocity stage, Newton solver pieces, barrier waits ...; enum CLK_* in csrc/km_common.cuh) into the
    caller's device buffer; NULL switches it off.  Only libraries built with -DKM_PHASE_CLOCKS record anything; the

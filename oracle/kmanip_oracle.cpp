@@ -1273,7 +1273,7 @@ static void ko_env_reset_(const ko_model* m, ko_data* d, const ko_task* t, const
 
 /* one env step: before_step; mj_step2; mj_step x (n_sub-1); mj_step1 */
 static void ko_env_step_(const ko_model* m, ko_data* d, const ko_task* t, const float* action, ko_ik_fn ik, void* user) {
-  int nsub = (int)std::lround(K_CONTROL_TIMESTEP / m->timestep);
+  int nsub = t->n_sub_steps > 0 ? t->n_sub_steps : (int)std::lround(K_CONTROL_TIMESTEP / m->timestep);
   ko_before_step(m, d, t, action, ik ? ik : ko_ik_default, user);
   ko_step2(m, d, 0);
   for (int i = 0; i < nsub - 1; i++) { ko_step1(m, d); ko_step2(m, d, 0); }

@@ -71,6 +71,8 @@ typedef struct ko_task {
   int ik_teleport;           /* reproduce ik_mujoco.py:34,67 leaving qpos[mask] at the solution */
   int max_episode_steps;     /* __init__.py:28 */
   int ik_mode;               /* device IK: 0 fixed-iteration projected LM, 1 restated scipy TRF (the oracle's own "trf" mode calls the real scipy) */
+  int n_sub_steps;           /* physics sub-steps per env step; 0 = round(CONTROL_TIMESTEP / timestep) (dm_control) */
+  int reserved0;
   double q_home[32];         /* float32-rounded home pose, __init__.py:53-122 */
   double cube_spawn_lo[3], cube_spawn_hi[3];   /* __init__.py:164-170 */
 } ko_task;

@@ -57,13 +57,13 @@ class Oracle:
     """One simulated env on the CPU, mirroring KManipTask + dm_control's episode loop."""
 
     def __init__(self, env_id: str = "KManipSoloArm", flat: Optional[dict] = None, ik_mode: str = "dls",
-                 ik_iters: int = K.DEVICE_IK_ITERS, ik_teleport: bool = True, flops: bool = False, **opt):
+                 ik_iters: int = K.DEVICE_IK_ITERS, ik_teleport: bool = True, flops: bool = False, n_sub_steps: int = 0, **opt):
         self.kw = K.ENV_REGISTRY[env_id]
         self.flat = dict(flat if flat is not None else mjcf.load_flat(mjcf.scene_of_mjcf(self.kw["mjcf_filename"])))
         if opt:
             self.flat["opt"] = dict(self.flat["opt"], **opt)
         self.pm = flatmodel.PackedModel(self.flat)
-        self.task = flatmodel.make_task(self.flat, self.kw, ik_iters=ik_iters, ik_teleport=ik_teleport)
+        self.task = flatmodel.make_task(self.flat, self.kw, ik_iters=ik_iters, ik_teleport=ik_teleport, n_sub_steps=n_sub_steps)
         self.L = lib(flops)
         self.d = C.c_void_p(self.L.ko_data_new(self.pm.ref()))
         self.nq, self.nv, self.nu = self.flat["nq"], self.flat["nv"], self.flat["nu"]

@@ -202,4 +202,17 @@ void hs_reset(void* h, unsigned long long seed, unsigned long long env_id, const
 int hs_field(void* h, const char* name, double* out, int cap) { return ((HostSimBase*)h)->field(name, out, cap); }
 // non-empty when the lanes of the emulated warp diverged at a collective (a hang or undefined behaviour on the GPU)
 const char* hs_fault(void* h) { return ((HostSimBase*)h)->fault.c_str(); }
+// self-test of the warp emulator: mode 0 runs uniform collectives, mode 1 lets half of the lanes skip a shuffle;
+// returns 1 when the emulator reported divergent collectives
+int hs_emu_selftest(int mode) {
+  km_emu::Warp w;
+  const bool ok = km_emu::run(w, [&](int lane) {
+    float v = (float)lane;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (mode == 0 || lane < 16) v += __shfl_sync(0xffffffffu, v, 0);
+    __syncwarp();
+    (void)v;
+  });
+  return ok ? 0 : 1;
+}
 }

@@ -12,6 +12,42 @@ def rel_err(a, b, floor=1e-3):
     return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), floor))
 
 
+# Per-component relative error: every component is compared on the scale of its own unit (a batch-max over a
+# record that mixes radians, metres of slider travel and a unit quaternion hides a 1e-3 relative error on a slider).
+# floor = the magnitude below which a component's error is measured absolutely (its typical scale).
+UNIT_FLOOR = dict(hinge=0.1, slide=0.01, cube_pos=0.1, quat=1.0,          # rad, m (0.03 m travel), m, -
+                  hinge_vel=1.0, slide_vel=0.01, cube_lin=0.1, cube_ang=1.0)  # rad/s, m/s, m/s, rad/s
+
+
+def component_floors(flat, nq, nv):
+    """Per-component floors for a qpos [nq] and a qvel [nv] record of a KManip scene (links first, free cube last)."""
+    jt = list(flat["jnt_type"])[: nv - 6]      # 3 hinge, 2 slide
+    fq = np.array([UNIT_FLOOR["hinge"] if t == 3 else UNIT_FLOOR["slide"] for t in jt] + [UNIT_FLOOR["cube_pos"]] * 3 + [UNIT_FLOOR["quat"]] * 4)
+    fv = np.array([UNIT_FLOOR["hinge_vel"] if t == 3 else UNIT_FLOOR["slide_vel"] for t in jt] + [UNIT_FLOOR["cube_lin"]] * 3 + [UNIT_FLOOR["cube_ang"]] * 3)
+    assert fq.size == nq and fv.size == nv
+    return fq, fv
+
+
+def comp_rel_err(a, b, floors):
+    """max over envs and components of |a - b| / max(|b|, floor of the component); a, b: [n, k]."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floors[None, :])))
+
+
+def comp_rel_err_per_env(a, b, floors):
+    """[n] per-env maximum over components of |a - b| / max(|b|, floor of the component)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floors[None, :]), axis=1)
+
+
+def rel_err_per_env(a, b, floor=1e-3):
+    """[n] per-env max |a - b| on the scale of the field's batch magnitude (the per-env resolution of rel_err)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b), axis=1) / max(float(np.max(np.abs(b))), floor)
+
+
 def pack_state(st):
     """Batch state dict -> [n, state_dim] records (include/kmanip_b200.h layout; cube_lo = 0)."""
     n = st["qpos"].shape[0]

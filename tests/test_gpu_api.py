@@ -82,23 +82,86 @@ def test_vector_env_autoreset_and_totals():
     assert env.observation_space.spaces["q_pos"].shape == (n, 20) and env.action_space.spaces["eer_pos"].shape == (n, 3)
     assert env.single_action_space.spaces["grip_l"].shape == (1,) and env.observation_space.contains({kk: v.cpu().numpy() for kk, v in obs.items()})
     gen = torch.Generator(device="cuda").manual_seed(0)
+    ret = torch.zeros(n, dtype=torch.float64, device="cuda")
+    tot = np.zeros(4)
+    prev_obs = None
     for t in range(k.MAX_EPISODE_STEPS + 2):
         flat = env.sample_actions(gen)
         act = {kk: flat[:, sl] for kk, sl in env.action_layout.items()}       # dict actions with the reference keys
         obs, rew, term, trunc, info = env.step(act)
+        if prev_obs is not None:     # default copy=True: what step() returned before is not overwritten by the next step
+            assert torch.equal(prev_obs[0]["q_pos"], prev_obs[1])
+        prev_obs = (obs, obs["q_pos"].clone())
         assert not term.any()
         assert bool(trunc.all()) == (t == k.MAX_EPISODE_STEPS - 1) and bool(trunc.any()) == (t == k.MAX_EPISODE_STEPS - 1)
         for v in obs.values():
             assert float(v.min()) >= -1 and float(v.max()) <= 1
+        # the batched `info` of reference env_base.py:243-250, produced by the step kernel
+        in_ep = t % k.MAX_EPISODE_STEPS + 1
+        assert (info["step"] == in_ep).all() and (info["episode"] == t // k.MAX_EPISODE_STEPS).all()
+        assert torch.allclose(info["sim_time"].double(), torch.full((n,), in_ep * k.CONTROL_TIMESTEP, dtype=torch.float64, device="cuda"), atol=1e-4)
+        assert torch.equal(info["is_success"], rew > k.REWARD_SUCCESS_THRESHOLD)
+        ret += rew.double()
+        assert torch.allclose(info["episode_return"].double() * (~trunc) + info["final_return"].double() * trunc, ret, rtol=1e-4, atol=1e-4)
+        tot += [float(rew.double().sum()), n, float(trunc.sum()), float(info["is_success"].sum())]
         if t == k.MAX_EPISODE_STEPS - 1:
             # same-step autoreset: obs is the first observation of the new episode, final_obs the last of the old one
             assert torch.equal(obs["q_pos"], first["q_pos"]) and torch.equal(obs["q_vel"], first["q_vel"])
             assert not torch.equal(obs["cube_pos"], first["cube_pos"])       # new spawn for episode 1
             assert not torch.equal(info["final_obs"]["q_pos"], first["q_pos"])
-            assert (info["final_return"] != 0).all()
-    tot = env.totals.cpu().numpy()
-    assert tot[1] == n * (k.MAX_EPISODE_STEPS + 2) and tot[2] == n
+            assert (info["final_return"] != 0).all() and torch.equal(info["final_return"], info["episode_return"])
+            ret.zero_()
+        else:
+            assert (info["final_return"] == 0).all()
+    got = env.totals.cpu().numpy()           # km_episode_stats: accumulated by the step kernel, no extra launches
+    assert got[1] == n * (k.MAX_EPISODE_STEPS + 2) and got[2] == n and got[3] == tot[3]
+    assert abs(got[0] - tot[0]) < 1e-3 * max(1.0, abs(tot[0]))
+    assert float(env.sim.episode_stats(reset=True)[1]) == got[1] and float(env.totals[1]) == 0
     env.close()
+
+
+@pytest.mark.gpu
+def test_vector_env_step_is_one_kernel_launch():
+    """copy=False: step() returns views into the simulator's buffers and launches exactly ONE kernel -- the step kernel
+    (km_launch_count, and the CUDA activity of the call as the torch profiler sees it, when CUPTI is available)."""
+    import torch
+    n = 256
+    env = k.make_vec("KManipSoloArmQPos", n, dtype="float32", seed=1, copy=False)
+    env.reset()
+    act = env.sample_actions(torch.Generator(device="cuda").manual_seed(0))
+    env.step(act)
+    l0 = env.sim.launches
+    obs, rew, term, trunc, info = env.step(act)
+    assert env.sim.launches - l0 == 1
+    assert obs["q_pos"].data_ptr() == env.sim.obs.data_ptr() and rew.data_ptr() == env.sim.reward.data_ptr()
+    assert info["step"].data_ptr() == env.sim.step_count.data_ptr()
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            env.step(act)
+            torch.cuda.synchronize()
+        kernels = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "memcpy" not in e.name.lower() and "memset" not in e.name.lower()]
+    except Exception:
+        kernels = None
+    if kernels:      # CUPTI present: the only kernel of the call is ours
+        assert len(kernels) == 1 and "k_env_step" in kernels[0], kernels
+    env.close()
+
+
+@pytest.mark.gpu
+def test_batch_sim_argument_validation():
+    import torch
+    from gym_kmanip_b200.batch_sim import BatchSim
+    with pytest.raises(ValueError):
+        BatchSim("KManipSoloArm", 8, dtype="fp32")
+    sim = BatchSim("KManipSoloArm", 8, dtype="float32")
+    sim.reset()
+    with pytest.raises(ValueError):
+        sim.reset(mask=torch.ones(7, dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        sim.step(torch.zeros(8, sim.act_dim + 1))
+    sim.step(torch.zeros(8, sim.act_dim))          # a CPU tensor is moved to the handle's device
+    sim.close()
 
 
 @pytest.mark.gpu
