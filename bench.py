@@ -45,7 +45,24 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--ik-mode", type=int, default=0, help="0: fast fixed-iteration LM IK (default of the batched path); 1: exact-parity scipy-TRF restatement")
+    p.add_argument("--no-extra", action="store_true", help="skip the other BASELINE.json configurations (extra_configs)")
     return p.parse_args()
+
+
+def config_of(a):
+    """`config` of the JSON line: identical for our arm and the reference arm (same workload, same batch)."""
+    return {"workload": workload_name(a), "envs_per_gpu": a.envs, "sub_steps_per_env_step": 10}
+
+
+# the other BASELINE.json configurations, measured on one GPU after the headline (env id, envs, dtype, BASELINE config)
+EXTRA_CONFIGS = [
+    ("KManipSoloArm", 8192, "float32", "configs[2]: SoloArm + IK + cube contacts, 65536 envs across 8 GPUs = 8192 per GPU"),
+    ("KManipSoloArm", 65536, "float32", "configs[2] total batch on one GPU"),
+    ("KManipDualArm", 32768, "float32", "configs[3]: DualArm + 2 IK solves, 32768 envs per GPU"),
+    ("KManipTorso", 16384, "float64", "configs[4]: Torso, fp64 validation build, 16384 envs per GPU"),
+    ("KManipSoloArmQPos", 65536, "float32", "throughput batch of the headline workload"),
+]
+NOMINAL_FMA_TFLOPS = {"float32": 74.4, "float64": 37.2}    # 148 SMs x 128 (64) lanes x 2 x 1.965 GHz (SURVEY.md 8d)
 
 
 def workload_name(a):
@@ -60,7 +77,6 @@ def cpu_leg(env_id: str, n: int, budget_s: float, threads: int):
     from oracle import oracle as om
     om.build()
     o = om.Oracle(env_id)
-    n = min(n, max(threads * 32, 64))
     st = om.batch_reset_state(o, n, seed=0)
     if o.nmocap == 0:
         st["mocap"] = np.zeros((n, 0))
@@ -99,7 +115,9 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": a.envs / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": workload_name(a), "note": "CPU oracle port of the reference path; real MuJoCo is not installable here"},
+        "data": "synthetic", "config": config_of(a),
+        "timing": "host wall clock (time.perf_counter) around the CPU loop: this arm has no device",
+        "note": "CPU oracle port of the reference path on all host threads; real MuJoCo is not installable here (BASELINE.md)",
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
@@ -136,8 +154,69 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def fma_peak(local, f32):
+    """FMA throughput of the CUDA-core pipe measured on this GPU right now (km_measure_fma_peak), TFLOP/s, or None."""
+    import ctypes as C
+    from gym_kmanip_b200 import _lib
+    pk = C.c_double(0)
+    rc = _lib.load().km_measure_fma_peak(local, 32 if f32 else 64, C.byref(pk))
+    return pk.value if rc == 0 and pk.value > 0 else None
+
+
+def fp_roofline(env, dtype, n, ms_per_step, measured_peak, flops):
+    """FP-pipe roofline of one configuration: counted algorithmic FLOPs / launch time against the measured FMA peak of
+    this run AND the nominal peak (74.4 TFLOP/s fp32, 37.2 fp64 at the 1965 MHz maximum SM clock)."""
+    fl = flops.get(env)
+    if not fl:
+        return None
+    ach = fl * n / (ms_per_step * 1e-3) / 1e12
+    nominal = NOMINAL_FMA_TFLOPS[dtype]
+    return {"bound": "fp32" if dtype == "float32" else "fp64", "achieved": ach, "peak": measured_peak or nominal, "unit": "TFLOP/s",
+            "frac": ach / (measured_peak or nominal), "frac_of_nominal": ach / nominal, "peak_nominal": nominal,
+            "flop_per_env_step": fl,
+            "peak_source": "measured (km_measure_fma_peak, dependent-FMA chains, this run)" if measured_peak else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+            "flop_source": "counted by the oracle's operation-counting build (profiles/flops_per_env_step.json)"}
+
+
+def time_steps(sim, acts, steps, flush, torch):
+    """CUDA-event time of `steps` launches (L2 flushed between them, outside the event pairs); returns total ms."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        flush.fill_(i & 255)
+        evs[i][0].record()
+        sim.step(acts[i % acts.shape[0]], autoreset=True, contacts=False)
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    return sum(e0.elapsed_time(e1) for e0, e1 in evs)
+
+
+def run_extra_configs(local, flush, flops, peaks, torch):
+    """The other BASELINE.json configurations on this GPU, a few steps each from step 24 of an episode (cube landed), so
+    that the driver-run JSON line -- not only profiles/ -- carries them."""
+    from gym_kmanip_b200.batch_sim import BatchSim
+    out = []
+    for env, n, dtype, what in EXTRA_CONFIGS:
+        try:
+            sim = BatchSim(env, n, device=local, dtype=dtype, seed=0)
+            sim.reset()
+            gen = torch.Generator(device=sim.device).manual_seed(99)
+            acts = torch.rand(8, n, sim.act_dim, device=sim.device, generator=gen) * 2 - 1
+            for i in range(24):
+                sim.step(acts[i % 8], autoreset=True, contacts=False)
+            torch.cuda.synchronize()
+            k = 8
+            ms = time_steps(sim, acts, k, flush, torch) / k
+            out.append({"baseline_config": what, "env": env, "envs": n, "dtype": dtype, "steps": k, "ms_per_step": ms,
+                        "value": n / (ms * 1e-3), "unit": UNIT, "launch": sim.launch_config(),
+                        "roofline_fp": fp_roofline(env, dtype, n, ms, peaks.get(dtype), flops)})
+            sim.close()
+            del sim, acts
+        except Exception as e:   # a configuration that cannot run must not take the headline line with it
+            out.append({"baseline_config": what, "env": env, "envs": n, "dtype": dtype, "error": repr(e)})
+    return out
+
+
 def run_ours(a):
-    import numpy as np
     import torch
     import torch.distributed as dist
     from gym_kmanip_b200.batch_sim import BatchSim
@@ -166,28 +245,19 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    ret_sum = torch.zeros(4, dtype=torch.float64, device=dev)   # sum reward, steps, truncations, successes
     for i in range(a.warmup):
         sim.step(acts[i % nact], autoreset=True, contacts=False)
+    sim.episode_stats(reset=True)          # the rollout totals are accumulated by the step kernel itself (km_episode_stats)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = sim.launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     t_wall = time.perf_counter()
-    for i in range(a.steps):
-        flush.fill_(i & 255)                       # L2 flush between timed iterations (outside the event pair)
-        evs[i][0].record()
-        obs, rew, term, trunc = sim.step(acts[i % nact], autoreset=True, contacts=False)
-        evs[i][1].record()
-        ret_sum[0] += rew.sum(dtype=torch.float64)
-        ret_sum[1] += n
-        ret_sum[2] += trunc.sum(dtype=torch.float64)
-        ret_sum[3] += (rew > 2.0).sum(dtype=torch.float64)
+    dev_ms = time_steps(sim, acts, a.steps, flush, torch)
     barrier()
     t_wall = time.perf_counter() - t_wall
     launches = sim.launches - l0
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    ret_sum = sim.episode_stats()          # [sum of rewards, env steps, truncations, success steps] of the timed steps
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -230,8 +300,9 @@ def run_ours(a):
         except Exception:
             pass
         hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
-        # algorithmic HBM bytes per env-step: state record in + out, action in, obs + reward + flag out
-        alg_bytes = 2 * sim.state_dim * esize + 2 * 4 * 2 + sim.act_dim * 4 + sim.obs_dim * esize + esize + 1
+        # algorithmic HBM bytes per env-step: state record in + out, running return in + out, action in,
+        # obs + reward + flag out
+        alg_bytes = 2 * sim.state_dim * esize + 2 * 4 * 2 + 2 * esize + sim.act_dim * 4 + sim.obs_dim * esize + esize + 1
         ms_per_step = dev_ms / a.steps
         achieved = alg_bytes * n / (ms_per_step * 1e-3) / 1e9
         flops = {}
@@ -239,45 +310,40 @@ def run_ours(a):
             flops = json.load(open(os.path.join(ROOT, "profiles", "flops_per_env_step.json")))
         except Exception:
             pass
-        fl = flops.get(a.env)
-        fp32 = None
-        if fl:
-            # denominator: FMA throughput of the CUDA-core pipe measured on this GPU right now (km_measure_fma_peak)
-            import ctypes as C
-            from gym_kmanip_b200 import _lib
-            pk = C.c_double(0)
-            f32 = sim.tdtype == torch.float32
-            rc = _lib.load().km_measure_fma_peak(local, 32 if f32 else 64, C.byref(pk))
-            fp_peak, src = (pk.value, "measured (km_measure_fma_peak, dependent-FMA chains, this run)") if rc == 0 and pk.value > 0 else \
-                ((74.4 if f32 else 37.2), "nominal 148 SM x 128 lanes x 2 x 1.965 GHz")
-            ach = fl * n / (ms_per_step * 1e-3) / 1e12
-            fp32 = {"bound": "fp32" if f32 else "fp64", "achieved": ach, "peak": fp_peak, "unit": "TFLOP/s",
-                    "frac": ach / fp_peak, "flop_per_env_step": fl, "peak_source": src,
-                    "flop_source": "counted by the oracle's operation-counting build (profiles/flops_per_env_step.json)"}
+        fma = {"float32": fma_peak(local, True), "float64": fma_peak(local, False)}
+        traffic = flops.get("dram_traffic_bytes_per_launch", {}).get(f"{a.env}:{n}:{cfg['lanes_per_env']}")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if sim.tdtype == torch.float32 else "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "envs_per_gpu": n, "l2": "flushed between timed iterations (256 MiB fill)",
-                       "launch": cfg, "sub_steps_per_env_step": 10},
+            "config": config_of(a),
+            "timing": "CUDA events on the launching stream around every launch; L2 flushed (256 MiB fill) between timed launches, outside the event pairs; max over ranks",
+            "launch": cfg,
             "sub_steps_per_s": value * 10,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": flops.get("dram_traffic_bytes_per_launch", {}).get(f"{a.env}:{n}:{cfg['lanes_per_env']}"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": alg_bytes,
+                         "traffic": traffic,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the same command, from profiles/ (not measured in this run)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": alg_bytes,
                          "note": "the path is FP-pipe/latency bound by construction (SURVEY.md 8d); see roofline_fp"},
-            "roofline_fp": fp32,
-            "episode_stats": {"mean_reward": float(ret_sum[0] / ret_sum[1]), "truncations": float(ret_sum[2]), "successes": float(ret_sum[3])},
+            "roofline_fp": fp_roofline(a.env, a.dtype, n, ms_per_step, fma.get(a.dtype), flops),
+            "episode_stats": {"mean_reward": float(ret_sum[0] / max(float(ret_sum[1]), 1.0)), "env_steps": float(ret_sum[1]),
+                              "truncations": float(ret_sum[2]), "successes": float(ret_sum[3]),
+                              "source": "accumulated by the step kernel (km_episode_stats)"},
             "wall_s_timed_region": t_wall,
         }
+        sim.close()
+        if world == 1 and not a.no_extra:
+            line["extra_configs"] = run_extra_configs(local, flush, flops, fma, torch)
         if not a.no_cpu and world == 1:
             cores = os.cpu_count() or 1
             v, sample = cpu_leg(a.env, n, a.cpu_seconds, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
-    sim.close()
+    else:
+        sim.close()
     if world > 1:
         dist.destroy_process_group()
 
