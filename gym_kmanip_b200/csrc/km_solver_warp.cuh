@@ -201,6 +201,14 @@ template <class S, typename T, class E> struct WarpSolver {
     const unsigned pm = __ballot_sync(FULL, isedge && (SH ? jar[EA] < T(0) : q0));
     const unsigned nm = __ballot_sync(FULL, isedge && (SH ? jar[EA + 1] < T(0) : q1));
     const bool refactor = __any_sync(FULL, isarm && hd != hd_cached);
+    // The cube block depends on the states of the pyramid rows (pm, nm) and of the cube's friction-loss rows only: when
+    // none of them changed since the previous iteration (the usual case once the active set has settled) its factor in
+    // e.c.H / dinv is still valid and the rebuild is skipped
+    int* key = e.c.efc_state;
+    const bool rebuild = __any_sync(FULL, (iscube && hd != hd_cached) || (unsigned)key[0] != pm || (unsigned)key[1] != nm);
+    if (refactor || rebuild) g.sync();
+    if (rebuild) {
+    if (lane == 0) { key[0] = (int)pm; key[1] = (int)nm; }
     // cube block: diag + sum over contacts of Jq^T W Jq, one lower-triangle entry (ei, ej) per lane
     const int t = (lane < 21 ? lane : 20) + opaque_zero();
     const int ei = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15), ej = t - ei * (ei + 1) / 2;
@@ -225,8 +233,7 @@ template <class S, typename T, class E> struct WarpSolver {
       e.c.H[NVA + ej][ei] = h;
     }
     g.sync();
-    T w[6], dw = 1;
-    sfor<0, 6>([&](auto J) { constexpr int j = decltype(J)::value; w[j] = e.c.H[iscube ? dofi : NVA][j]; });
+    }
     if (refactor) {   // warp-uniform (a vote): a friction-loss or limit row of the arm changed state
       T row[BS], dsave = dinv;
       sfor<0, BS>([&](auto J) {
@@ -234,14 +241,20 @@ template <class S, typename T, class E> struct WarpSolver {
         const T mv = e.M[isarm ? dofi : 0][isarm ? b0 + (j < bn ? j : 0) : 0];
         row[j] = isarm ? (j < bn ? mv + (j == li ? hd : T(0)) : T(0)) : (j == li ? T(1) : T(0));
       });
-      hd_cached = hd;
+      hd_cached = isarm ? hd : hd_cached;
       factor_blocks(row);
       dinv = isarm ? dinv : dsave;
       store_rows<BS>(row, isarm);
     }
-    factor_cube(w, &dw);
-    dinv = iscube ? dw : dinv;
-    store_rows<6>(w, iscube);
+    if (rebuild) {
+      T w[6], dw = 1;
+      sfor<0, 6>([&](auto J) { constexpr int j = decltype(J)::value; w[j] = e.c.H[iscube ? dofi : NVA][j]; });
+      g.sync();
+      hd_cached = iscube ? hd : hd_cached;
+      factor_cube(w, &dw);
+      dinv = iscube ? dw : dinv;
+      store_rows<6>(w, iscube);
+    }
     { const T x = solve(grad); search = isdof ? -x : T(0); }   // every lane takes part in the shuffles
   }
 
@@ -346,6 +359,7 @@ template <class S, typename T, class E> struct WarpSolver {
     qs = isdof ? e.qfrc_smooth[dofi] : T(0);
     // ---- smooth acceleration: factor M (every block), qacc_smooth = M^{-1} qfrc_smooth
     dinv = 1; hd_cached = 0;
+    if (lane == 0) { e.c.efc_state[0] = -1; e.c.efc_state[1] = -1; }   // no cube-block factor yet (pm = ~0 cannot occur)
     {
       T row[BS];
       sfor<0, BS>([&](auto J) {
