@@ -103,6 +103,21 @@ template <typename T> KM_HD T tmax(T a, T b) { return a > b ? a : b; }
 template <typename T> KM_HD T tmin(T a, T b) { return a < b ? a : b; }
 template <typename T> KM_HD T tclip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
+KM_HD int popc(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+KM_HD int ffs1(unsigned x) {   // 1-based index of the lowest set bit, 0 if none
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x);
+#else
+  return __builtin_ffs((int)x);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------- lane group
 template <int G> struct Grp {
   int lane;        // 0..G-1 inside the group
@@ -171,6 +186,17 @@ template <int G> struct Grp {
 #endif
     return v;
   }
+  // bit i set: lane i of the group voted true
+  KM_HD unsigned ballot(bool p) const {
+#if KM_WARP_CODE
+    if (G == 1) return p ? 1u : 0u;
+    if (G == 32) return __ballot_sync(0xffffffffu, p);
+    const unsigned b = __ballot_sync(mask, p) & mask;
+    return b >> (ffs1(mask) - 1);
+#else
+    return p ? 1u : 0u;
+#endif
+  }
   KM_HD bool any(bool p) const {
 #if KM_WARP_CODE
     if (G == 1) return p;
@@ -223,6 +249,12 @@ template <typename T> KM_HD void qmul(T* r, const T* a, const T* b) {
   T t2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
   T t3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
   r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+// r = q v q^-1 for a unit quaternion: v + 2 u x (u x v + w v)
+template <typename T> KM_HD void qrot(T* r, const T* q, const T* v) {
+  const T tx = q[2] * v[2] - q[3] * v[1] + q[0] * v[0], ty = q[3] * v[0] - q[1] * v[2] + q[0] * v[1], tz = q[1] * v[1] - q[2] * v[0] + q[0] * v[2];
+  const T x = v[0] + T(2) * (q[2] * tz - q[3] * ty), y = v[1] + T(2) * (q[3] * tx - q[1] * tz), z = v[2] + T(2) * (q[1] * ty - q[2] * tx);
+  r[0] = x; r[1] = y; r[2] = z;
 }
 // rotation matrix (row-major) of a unit quaternion (mju_quat2Mat)
 template <typename T> KM_HD void q2mat(T* m, const T* q) {

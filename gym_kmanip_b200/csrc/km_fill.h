@@ -93,6 +93,7 @@ template <class S, typename T> int fill_model(const km_model* fm, const km_task*
     total_mass += fm->body_mass[b];
     for (int i = 0; i < 3; i++) { m.ipos[l][i] = (T)fm->body_ipos[3 * b + i]; m.inertia[l][i] = (T)fm->body_inertia[3 * b + i]; }
     m.range[l][0] = (T)fm->jnt_range[2 * l]; m.range[l][1] = (T)fm->jnt_range[2 * l + 1];
+    KM_FILL_CHECK(fm->jnt_range[2 * l] < fm->jnt_range[2 * l + 1], "joint range must be lo < hi (a joint violates at most one side)");
     m.dk_range[l][0] = fm->jnt_range[2 * l]; m.dk_range[l][1] = fm->jnt_range[2 * l + 1];
     m.lim_invw[l] = (T)fm->dof_invweight0[l];
     for (int i = 0; i < 2; i++) m.lim_solref[l][i] = (T)fm->jnt_solref[2 * l + i];

@@ -24,6 +24,57 @@ KM_TPL KM_FN void kinematics(KM_ARGS) {
     qnormalize(e.qpos + D::NVA + 3);
     q2mat(e.cmat, e.qpos + D::NVA + 3);
   }
+#if KM_WARP_CODE
+  if constexpr (G >= D::NVA && G > 1) {
+    // One link per lane.  Every link first forms its transform relative to its parent (joint included), then the
+    // transforms are composed up the tree by pointer jumping: after round r a link's transform is relative to its
+    // 2^r-th ancestor (or the world), so four rounds cover chains of up to 16 links -- ~300 warp-instructions with all
+    // links busy instead of one lane walking the ten levels (~1 400).  Compared with walking the chain link by link the
+    // products associate differently (and the quaternion is normalised once, at the end): differences of a few ulp.
+    static_assert(D::MAXLEVEL <= 16, "four pointer-jumping rounds");
+    const int l = g.lane < D::NVA ? g.lane : D::NVA - 1;   // surplus lanes shadow the last link (they take part in the shuffles)
+    const T th = e.qpos[l];
+    T q[4] = {m.lquat[l][0], m.lquat[l][1], m.lquat[l][2], m.lquat[l][3]}, p[3] = {m.lpos[l][0], m.lpos[l][1], m.lpos[l][2]};
+    if (m.jtype[l] == JT_HINGE) {   // rotate about local z: q <- q * (c, 0, 0, s)
+      T s, c;
+      N::sincos(th * T(0.5), &s, &c);
+      const T t0 = q[0] * c - q[3] * s, t1 = q[1] * c + q[2] * s, t2 = q[2] * c - q[1] * s, t3 = q[3] * c + q[0] * s;
+      q[0] = t0; q[1] = t1; q[2] = t2; q[3] = t3;
+    } else {                        // slide along local z
+      const T z[3] = {0, 0, th};
+      T d[3];
+      qrot(d, q, z);
+      p[0] += d[0]; p[1] += d[1]; p[2] += d[2];
+    }
+    int anc = m.parent[l];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int src = anc >= 0 ? anc : l;
+      T qa[4], pa[3];
+      for (int i = 0; i < 4; i++) qa[i] = g.shfl(q[i], src);
+      for (int i = 0; i < 3; i++) pa[i] = g.shfl(p[i], src);
+      const int anc2 = g.shfl(anc, src);
+      if (anc >= 0) {
+        T t[3], qq[4];
+        qrot(t, qa, p);
+        p[0] = pa[0] + t[0]; p[1] = pa[1] + t[1]; p[2] = pa[2] + t[2];
+        qmul(qq, qa, q);
+        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+        anc = anc2;
+      }
+    }
+    qnormalize(q);
+    T mat[9];
+    q2mat(mat, q);
+    if (g.lane < D::NVA) {
+      for (int i = 0; i < 4; i++) e.xquat[l][i] = q[i];
+      for (int i = 0; i < 9; i++) e.xmat[l][i] = mat[i];
+      for (int i = 0; i < 3; i++) e.xpos[l][i] = p[i];
+    }
+    g.sync();
+    return;
+  }
+#endif
   for (int lv = 0; lv < m.nlevel; lv++) {
     for (int k = m.level_adr[lv] + g.lane; k < m.level_adr[lv + 1]; k += G) {
       const int l = m.level_link[k], p = m.parent[l];
@@ -362,7 +413,35 @@ KM_TPL KM_FN void make_constraint(KM_ARGS) {
   typedef Dim<S> D;
   typedef Num<T> N;
   const T* cpos = e.qpos + D::NVA;
-  if (g.lane == 0) {
+#if KM_WARP_CODE
+  constexpr bool kLaneLimits = G >= D::NVA && G > 1;
+#else
+  constexpr bool kLaneLimits = false;
+#endif
+  if constexpr (kLaneLimits) {
+    // one joint per lane (a joint violates at most one side of its range, km_fill.h checks lo < hi); the active rows are
+    // numbered in joint order by a ballot, as the serial loop below numbers them
+    const int j = g.lane < D::NVA ? g.lane : D::NVA - 1;
+    const T q = e.qpos[j];
+    const T d0 = q - m.range[j][0], d1 = m.range[j][1] - q;
+    const bool on = g.lane < D::NVA && (d0 < T(0) || d1 < T(0));
+    const int side = d0 < T(0) ? 0 : 1;
+    const T dist = side == 0 ? d0 : d1;
+    const unsigned act = g.ballot(on);
+    const int r = D::NFRIC + popc(act & ((1u << g.lane) - 1u));
+    if (g.lane < D::NVA) e.dof_lim[j] = on ? r : -1;
+    if (on) {
+      T omi;
+      const T imp = impedance(m.lim_solimp[j], dist, &omi);
+      const T R = tmax(N::minval(), omi * m.lim_invw[j] / imp);
+      const T tc = tmax(m.lim_solref[j][0], T(2) * m.h), dr = m.lim_solref[j][1], dmax = m.lim_solimp[j][1];
+      e.efc_desc[r] = efc_pack(EFC_LIMIT, j, 0, side);
+      e.efc_D[r] = T(1) / R;
+      e.lim_B[r - D::NFRIC] = T(2) / (dmax * tc);
+      e.lim_Kip[r - D::NFRIC] = (T(1) / (dmax * dmax * tc * tc * dr * dr)) * imp * dist;
+    }
+    if (g.lane == 0) { e.nlim = popc(act); e.nefc = D::NFRIC + popc(act) + 6 * e.ncon; }
+  } else if (g.lane == 0) {
     int r = D::NFRIC;
     for (int j = 0; j < D::NVA; j++) {
       const T q = e.qpos[j];

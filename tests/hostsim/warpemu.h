@@ -131,4 +131,6 @@ KM_EMU_NI inline bool __all_sync(unsigned, bool p) {
   for (int i = 0; i < 32; i++) r = r && (b[i] & 1u);
   return r;
 }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 KM_EMU_NI inline void __syncwarp(unsigned = 0xffffffffu) { km_emu::exchange(0, km_emu::K_SYNC, KM_EMU_SITE); }
