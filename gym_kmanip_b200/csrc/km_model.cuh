@@ -54,6 +54,14 @@ template <class S> constexpr int blk_end(int j) {
   return e;
 }
 
+template <class S> constexpr int blk_begin(int j) { return j >= S::NVA ? S::NVA : dof_root<S>(j); }
+// largest diagonal block (longest kinematic chain, at least the cube's 6)
+template <class S> constexpr int max_block() {
+  int mx = 6;
+  for (int j = 0; j < S::NVA; j++) mx = blk_end<S>(j) - blk_begin<S>(j) > mx ? blk_end<S>(j) - blk_begin<S>(j) : mx;
+  return mx;
+}
+
 // -------------------------------------------------------------------------------------------- model
 template <class S, typename T> struct Model {
   typedef Dim<S> D;

@@ -12,6 +12,16 @@
 namespace km {
 
 // E is the env working-set type (Env<S, T, TPE>); it is always deduced from the argument
+// A/B switches of the one-link-per-lane formulations of the smooth phases (warp-per-env kernels)
+#ifndef KM_PAR_KIN
+#define KM_PAR_KIN 1
+#endif
+#ifndef KM_PAR_CRB
+#define KM_PAR_CRB 1
+#endif
+#ifndef KM_PAR_VEL
+#define KM_PAR_VEL 1
+#endif
 #define KM_TPL template <class S, typename T, int G, class E>
 #define KM_ARGS E& e, const Model<S, T>& m, const Grp<G>& g
 
@@ -24,7 +34,7 @@ KM_TPL KM_FN void kinematics(KM_ARGS) {
     qnormalize(e.qpos + D::NVA + 3);
     q2mat(e.cmat, e.qpos + D::NVA + 3);
   }
-#if KM_WARP_CODE
+#if KM_WARP_CODE && KM_PAR_KIN
   if constexpr (G >= D::NVA && G > 1) {
     // One link per lane.  Every link first forms its transform relative to its parent (joint included), then the
     // transforms are composed up the tree by pointer jumping: after round r a link's transform is relative to its
@@ -105,9 +115,98 @@ KM_TPL KM_FN void kinematics(KM_ARGS) {
   }
 }
 
+#if KM_WARP_CODE
+// One link per lane (G >= NVA).  v[0..N) <- sum of v over the links of the own link's SUBTREE: links are numbered depth
+// first, so a subtree is the index range [l, sub_end[l]) inside the link's kinematic chain block; a suffix scan over the
+// block (four rounds) minus the suffix that starts behind the subtree (only the later siblings' subtrees: comparable
+// magnitudes, no cancellation against the rest of the arm).
+template <class S, typename T, int G, int N> KM_HD void subtree_sum(T* v, int l, const Model<S, T>& m, const Grp<G>& g) {
+  const int be = m.blk0[l] + m.blkn[l], se = m.sub_end[l];
+#pragma unroll
+  for (int d = 1; d < max_block<S>(); d *= 2) {
+    const bool ok = l + d < be && g.lane < S::NVA;
+    const int src = ok ? g.lane + d : g.lane;
+#pragma unroll
+    for (int k = 0; k < N; k++) { const T t = g.shfl(v[k], src); v[k] = ok ? v[k] + t : v[k]; }
+  }
+  const bool cut = se < be && g.lane < S::NVA;
+  const int src = cut ? se : g.lane;
+#pragma unroll
+  for (int k = 0; k < N; k++) { const T t = g.shfl(v[k], src); v[k] = cut ? v[k] - t : v[k]; }
+}
+// v[0..N) <- sum of v over the own link and all its ancestors (pointer jumping up the tree, four rounds)
+template <class S, typename T, int G, int N> KM_HD void path_sum(T* v, int l, const Model<S, T>& m, const Grp<G>& g) {
+  int anc = m.parent[l];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int src = anc >= 0 ? anc : g.lane;
+    const int anc2 = g.shfl(anc, src);
+#pragma unroll
+    for (int k = 0; k < N; k++) { const T t = g.shfl(v[k], src); v[k] = anc >= 0 ? v[k] + t : v[k]; }
+    anc = anc >= 0 ? anc2 : anc;
+  }
+}
+#endif
+
 // mj_comPos: robot-tree centre of mass, cinert and cdof about it; mj_crb: mass matrix.
 KM_TPL KM_FN void com_crb(KM_ARGS) {
   typedef Dim<S> D;
+#if KM_WARP_CODE && KM_PAR_CRB
+  if constexpr (G >= D::NVA && G > 1) {
+    // one link per lane: centre of mass by a group sum, composite inertias by subtree sums in registers, then the mass
+    // matrix entries (link, ancestor) dealt over all lanes
+    const bool on = g.lane < D::NVA;
+    const int l = on ? g.lane : D::NVA - 1;
+    T xi[3];
+    mulv3(xi, e.xmat[l], m.ipos[l]);
+    for (int k = 0; k < 3; k++) xi[k] += e.xpos[l][k];
+    T com[3];
+    for (int k = 0; k < 3; k++) com[k] = g.sum(on ? m.mass[l] * xi[k] : T(0)) * m.total_mass_inv;
+    if (g.lane < 3) e.com[g.lane] = com[g.lane];
+    T off[3] = {xi[0] - com[0], xi[1] - com[1], xi[2] - com[2]}, ci[10], cd[6];
+    inert_com(ci, m.inertia[l], e.xmat[l], off, m.mass[l]);
+    const T ax[3] = {e.xmat[l][2], e.xmat[l][5], e.xmat[l][8]};
+    if (m.jtype[l] == JT_SLIDE) { cd[0] = 0; cd[1] = 0; cd[2] = 0; cd[3] = ax[0]; cd[4] = ax[1]; cd[5] = ax[2]; }
+    else {
+      const T o[3] = {com[0] - e.xpos[l][0], com[1] - e.xpos[l][1], com[2] - e.xpos[l][2]};
+      T c[3];
+      cross3(c, ax, o);
+      cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2]; cd[3] = c[0]; cd[4] = c[1]; cd[5] = c[2];
+    }
+    if (on) {
+      for (int i = 0; i < 10; i++) e.a.cinert[l][i] = ci[i];
+      for (int i = 0; i < 6; i++) e.a.cdof[l][i] = cd[i];
+    }
+    g.sync();
+    // composite inertia of every link's subtree: (link, component) items dealt over all lanes, summed link by link in
+    // index order (no scan here: a suffix-minus-suffix form cancels in float32 and the mass matrix of the light distal
+    // links is already a difference of large parallel-axis terms)
+    T* crb = &e.a.cvel[0][0];                        // cvel / cdof_dot are free until the velocity stage: 12 NVA words
+    KM_FOR(w, D::NVA * 10) {
+      const int i = w / 10, k = w - i * 10;
+      T sacc = e.a.cinert[i][k];
+      for (int c = i + 1; c < m.sub_end[i]; c++) sacc += e.a.cinert[c][k];
+      crb[w] = sacc;
+    }
+    g.sync();
+    for (int k = 0; k < 10; k++) ci[k] = crb[l * 10 + k];
+    T buf[6];
+    mul_inert_vec(buf, ci, cd);
+    if (on) for (int i = 0; i < 6; i++) e.a.cfrc[l][i] = buf[i];   // (cfrc is free until the velocity stage)
+    g.sync();
+    KM_FOR(w, D::NVA * (D::NVA + 1) / 2) {
+      const int ij = m.pair_ij[w], i = ij >> 8, j = ij & 255;    // the first NVA (NVA + 1) / 2 pairs are the links' lower triangle
+      if ((m.ancmask[i] >> j) & 1u) {
+        T s = 0;
+        for (int k = 0; k < 6; k++) s += e.a.cdof[j][k] * e.a.cfrc[i][k];
+        e.M[i][j] = s;
+        e.M[j][i] = s;
+      }
+    }
+    g.sync();
+    return;
+  }
+#endif
   KM_FOR(k, 3) {
     T s = 0;
     for (int l = 0; l < D::NVA; l++)
@@ -630,6 +729,53 @@ KM_TPL KM_HD void fwd_position(KM_ARGS) {
 // mj_comVel + mj_rne(flg_acc = 0) + mj_referenceConstraint.
 KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
   typedef Dim<S> D;
+#if KM_WARP_CODE && KM_PAR_VEL
+  constexpr bool kLanePerLink = G >= D::NVA && G > 1;
+#else
+  constexpr bool kLanePerLink = false;
+#endif
+  if constexpr (kLanePerLink) {
+#if KM_WARP_CODE
+    // one link per lane, everything in registers: link velocities and the velocity-product accelerations by sums along the
+    // path to the root, the bias forces by subtree sums of the links' spatial forces
+    const bool on = g.lane < D::NVA;
+    const int l = on ? g.lane : D::NVA - 1, p = m.parent[l];
+    const T qv = e.qvel[l];
+    T cd[6], ci[10], v[6], y[6], a[6], f[6], t1[6], t2[6];
+    for (int k = 0; k < 6; k++) cd[k] = e.a.cdof[l][k];
+    for (int k = 0; k < 10; k++) ci[k] = e.a.cinert[l][k];
+    for (int k = 0; k < 6; k++) v[k] = cd[k] * qv;
+    path_sum<S, T, G, 6>(v, l, m, g);                       // cvel of the link
+    T vp[6], dd[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 6; k++) vp[k] = g.shfl(v[k], p >= 0 ? p : g.lane);
+    if (p >= 0) cross_motion(dd, vp, cd);                   // cdof_dot
+    for (int k = 0; k < 6; k++) y[k] = dd[k] * qv;
+    path_sum<S, T, G, 6>(y, l, m, g);
+    for (int k = 0; k < 3; k++) { a[k] = y[k]; a[3 + k] = y[3 + k] - m.grav[k]; }
+    mul_inert_vec(f, ci, a);
+    mul_inert_vec(t1, ci, v);
+    cross_force(t2, v, t1);
+    for (int k = 0; k < 6; k++) f[k] = on ? f[k] + t2[k] : T(0);
+    subtree_sum<S, T, G, 6>(f, l, m, g);
+    T s = 0;
+    for (int k = 0; k < 6; k++) s += cd[k] * f[k];
+    if (on) e.bias[l] = s;
+    if (g.lane >= D::NVA && g.lane < D::NV) {
+      // free cube with its COM at the body origin: bias = [-m g ; w x (I w)] (w in the body frame)
+      const int k = g.lane - D::NVA;
+      T sc;
+      if (k < 3) sc = -m.cube_mass * m.grav[k];
+      else {
+        const T* w = e.qvel + D::NVA + 3;
+        const T Iw[3] = {m.cube_inertia[0] * w[0], m.cube_inertia[1] * w[1], m.cube_inertia[2] * w[2]};
+        T c[3];
+        cross3(c, w, Iw);
+        sc = c[k - 3];
+      }
+      e.bias[g.lane] = sc;
+    }
+#endif
+  } else {
   KM_FOR(l, D::NVA) {
     T v[6] = {0, 0, 0, 0, 0, 0};
     for (int j = l; j >= 0; j = m.parent[j]) {
@@ -679,6 +825,7 @@ KM_TPL KM_FN void fwd_velocity(KM_ARGS) {
       }
     }
     e.bias[i] = s;
+  }
   }
   // reference acceleration of every row: aref = -B (J qvel) - K imp pos
   mul_J<S, T, G>(e, m, g, e.qvel, e.efc_jv);

@@ -21,12 +21,6 @@ namespace km {
 
 #if defined(__CUDACC__) || defined(KM_WARP_EMU)
 
-template <class S> constexpr int blk_begin(int j) { return j >= S::NVA ? S::NVA : dof_root<S>(j); }
-template <class S> constexpr int max_block() {
-  int mx = 6;
-  for (int j = 0; j < S::NVA; j++) mx = blk_end<S>(j) - blk_begin<S>(j) > mx ? blk_end<S>(j) - blk_begin<S>(j) : mx;
-  return mx;
-}
 
 template <class S, typename T, class E> struct WarpSolver {
   typedef Dim<S> D;
