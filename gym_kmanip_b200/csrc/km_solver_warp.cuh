@@ -22,7 +22,84 @@ namespace km {
 #if defined(__CUDACC__) || defined(KM_WARP_EMU)
 
 
-template <class S, typename T, class E> struct WarpSolver {
+// Coupled case (a finger pad touches the cube, well under 1 % of the env-steps -- but an env on the slow path stalls its
+// whole CTA at the next phase barrier): dense H = M + diag + sum_c J_c^T W_c J_c over all NV dofs, assembled entry by
+// entry over the lanes, factorised one row per lane (NV pivots by shuffles), no caching.
+template <class S, typename T, class E>
+KM_DN T warp_direction_dense(E& e, const Model<S, T>& m, int lane, int dofi, bool isdof, T hd, unsigned pm, unsigned nm, int ncon, T grad) {
+typedef Dim<S> D;
+typedef Num<T> N;
+constexpr int NV = D::NV, NVA = D::NVA, CL0 = NV <= 16 ? 16 : 0;
+constexpr unsigned FULL = 0xffffffffu;
+  T* hds = e.c.hdiag;
+  if (isdof) hds[lane] = hd;
+  __syncwarp(FULL);
+  for (int w = lane; w < NV * (NV + 1) / 2; w += 32) {
+    const int ij = m.pair_ij[w], i = ij >> 8, j = ij & 255;
+    T h;
+    if (i < NVA) h = e.M[i][j];
+    else h = i == j ? (i - NVA < 3 ? m.cube_mass : m.cube_inertia[i - NVA < 3 ? 0 : i - NVA - 3]) : T(0);
+    if (i == j) h += hds[i];
+    for (int c = 0; c < ncon; c++) {
+      const unsigned sup = e.con_sup[c];
+      if (((sup >> i) & 1u) && ((sup >> j) & 1u)) {
+        const T Dc = e.con_D[c];
+        const T ni = jc<S, T>(e, c, 0, i), nj = jc<S, T>(e, c, 0, j);
+        T cnt = 0, acc = 0;
+#pragma unroll
+        for (int k = 1; k < 4; k++) {
+          const T p = (pm >> (CL0 + 4 * c + k)) & 1u ? T(1) : T(0), q = (nm >> (CL0 + 4 * c + k)) & 1u ? T(1) : T(0);
+          const T muk = e.con_mu[c][k - 1];
+          const T ti = jc<S, T>(e, c, k, i), tj = jc<S, T>(e, c, k, j);
+          cnt += p + q;
+          acc += Dc * muk * (p - q) * (ni * tj + ti * nj) + Dc * muk * muk * (p + q) * ti * tj;
+        }
+        h += Dc * cnt * ni * nj + acc;
+      }
+    }
+    e.c.H[i][j] = h;
+    e.c.H[j][i] = h;
+  }
+  __syncwarp(FULL);
+  T row[NV], di = 1;
+  sfor<0, NV>([&](auto J) { constexpr int j = decltype(J)::value; row[j] = e.c.H[dofi][j]; });
+  __syncwarp(FULL);
+  sfor<0, NV>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const T ajj = __shfl_sync(FULL, row[j], j);
+    const T inv = N::rsqrt(tmax(ajj, N::minval()));
+    const T lij = row[j] * inv;
+    row[j] = lij;
+    di = dofi == j ? inv : di;
+    sfor<j + 1, NV>([&](auto K) {
+      constexpr int k = decltype(K)::value;
+      row[k] -= lij * __shfl_sync(FULL, lij, k);
+    });
+  });
+  sfor<0, NV>([&](auto J) { constexpr int j = decltype(J)::value; if (isdof && j <= dofi) e.c.H[dofi][j] = row[j]; });
+  __syncwarp(FULL);
+  T acc = grad, y = 0;
+  sfor<0, NV>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const T yj = __shfl_sync(FULL, acc * di, j);
+    y = dofi == j ? yj : y;
+    acc = dofi > j ? acc - row[j] * yj : acc;
+  });
+  T acc2 = y, x = 0;
+  sfor_rev<NV>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const T xj = __shfl_sync(FULL, acc2 * di, j);
+    x = dofi == j ? xj : x;
+    const T l = e.c.H[j][dofi];
+    acc2 = j > dofi ? acc2 - l * xj : acc2;
+  });
+  return isdof ? -x : T(0);
+}
+
+
+// CPL: the instantiation for envs whose cube touches a finger pad (pad contacts carry arm columns, H is dense).  It is a
+// separate instantiation so that the common one carries none of its state or code (28 warps per SM: 72 registers).
+template <class S, typename T, class E, bool CPL> struct WarpSolver {
   typedef Dim<S> D;
   typedef Num<T> N;
   static constexpr int NV = D::NV, NVA = D::NVA, BS = max_block<S>();
@@ -35,7 +112,8 @@ template <class S, typename T, class E> struct WarpSolver {
   const Model<S, T>& m;
   const Grp<32>& g;
   // roles
-  int lane, dofi, b0, bn, li, cl, cc, cb, ncon;
+  int lane, dofi, b0, bn, li, cl, cc, cb, ncon, cslot;
+  unsigned csup;
   bool isdof, isarm, iscube, iscon, isedge, has_f, has_l;
   // row constants: slot 0 = friction-loss row of the dof (or a pyramid edge on the solo-arm contact lanes), slot 1 = limit
   T cdiag, rf0, fl0, sg, mu, Dr[NS];
@@ -62,6 +140,10 @@ template <class S, typename T, class E> struct WarpSolver {
 #pragma unroll
     for (int k = 0; k < 6; k++) pb += jr[k] * xs()[NVA + k];
     pb = iscon ? pb : T(0);
+    if constexpr (CPL) {             // finger-pad contacts: arm columns of the base row (its dof support only)
+      if (iscon && cslot < D::NPAD)
+        for (int j = 0; j < NVA; j++) pb += ((csup >> j) & 1u) ? e.Ja[cslot][cb][j] * xs()[j] : T(0);
+    }
     const T p0 = __shfl_sync(0xffffffffu, pb, lane & ~3);
     out[0] = has_f ? xi : T(0);
     out[1] = has_l ? sg * xi : T(0);
@@ -100,6 +182,13 @@ template <class S, typename T, class E> struct WarpSolver {
       for (int c2 = 0; c2 < ncon; c2++)
 #pragma unroll
         for (int b = 0; b < 4; b++) qfc += e.Jq[c2][b][li] * fbs()[4 * c2 + b];
+    if constexpr (CPL) if (isarm)
+      for (int c2 = 0; c2 < ncon; c2++) {
+        const int sl = e.con_slot[c2];
+        if (sl < D::NPAD && ((e.con_sup[c2] >> lane) & 1u))
+#pragma unroll
+          for (int b = 0; b < 4; b++) qfc += e.Ja[sl][b][lane] * fbs()[4 * c2 + b];
+      }
     const T r = Ma - qs;
     grad = isdof ? r - qfc : T(0);
     c += T(0.5) * r * (qacc - as);
@@ -194,6 +283,7 @@ template <class S, typename T, class E> struct WarpSolver {
     const T hd = ((has_f && q0) ? Dr[0] : T(0)) + ((has_l && q1) ? Dr[1] : T(0));
     const unsigned pm = __ballot_sync(FULL, isedge && (SH ? jar[EA] < T(0) : q0));
     const unsigned nm = __ballot_sync(FULL, isedge && (SH ? jar[EA + 1] < T(0) : q1));
+    if constexpr (CPL) { search = warp_direction_dense<S, T>(e, m, lane, dofi, isdof, hd, pm, nm, ncon, grad); return; }
     const bool refactor = __any_sync(FULL, isarm && hd != hd_cached);
     // The cube block depends on the states of the pyramid rows (pm, nm) and of the cube's friction-loss rows only: when
     // none of them changed since the previous iteration (the usual case once the active set has settled) its factor in
@@ -330,6 +420,8 @@ template <class S, typename T, class E> struct WarpSolver {
     ncon = e.ncon;
     cl = lane - CL0; cc = (cl >> 2) & 3; cb = cl & 3;
     iscon = cl >= 0 && cl < 16 && cc < ncon;
+    cslot = (CPL && iscon) ? e.con_slot[cc] : D::NPAD;
+    csup = (CPL && iscon) ? e.con_sup[cc] : 0u;
     isedge = iscon && cb > 0;
     const int base = D::NFRIC + e.nlim;
     cdiag = iscube ? (li < 3 ? m.cube_mass : m.cube_inertia[li < 3 ? 0 : li - 3]) : T(0);
@@ -416,8 +508,8 @@ template <class S, typename T, class E> struct WarpSolver {
   }
 };
 
-template <class S, typename T, class E> KM_DN void fwd_acc_constraint_w(E& e, const Model<S, T>& m, const Grp<32>& g) {
-  WarpSolver<S, T, E> s(e, m, g);
+template <class S, typename T, bool CPL, class E> KM_DN void fwd_acc_constraint_w(E& e, const Model<S, T>& m, const Grp<32>& g) {
+  WarpSolver<S, T, E, CPL> s(e, m, g);
   s.run();
 }
 

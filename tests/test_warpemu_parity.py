@@ -68,6 +68,50 @@ def test_emulated_warp_single_sub_step_fp32_per_component(env_id):
     assert wp < 1e-5 and wv < 5e-4      # see test_gpu_parity.py::test_single_sub_step_parity_fp32_per_component
 
 
+@pytest.mark.parametrize("env_id", ["KManipSoloArm", "KManipDualArm", "KManipTorso"])
+def test_emulated_warp_finger_pad_contacts_match_oracle(env_id):
+    """Coupled case on the warp-per-env code: the cube is placed against the finger pads (in half of the cases on the table
+    too), so pad contacts couple the arm and cube blocks and the register-resident solver takes its dense path (up to
+    four contacts; beyond that the generic solver)."""
+    from oracle import oracle as om
+    o = om.Oracle(env_id)
+    hs = hostsim.HostSim(env_id, 64, lanes=32)
+    st0 = om.batch_reset_state(o, 1, seed=1)
+    rng = np.random.default_rng(3)
+    pads = [i for i, nm in enumerate(o.flat["geom_name"]) if nm.startswith("finger_pad")]
+    seen = 0
+    for trial in range(8):
+        qpos = st0["qpos"][0].copy()
+        qpos[: o.nu] += rng.uniform(-0.05, 0.05, o.nu) * (np.arange(o.nu) < o.nu)
+        rngs = np.array(o.flat["jnt_range"])[: o.nu]
+        qpos[: o.nu] = np.clip(qpos[: o.nu], rngs[:, 0] + 1e-3, rngs[:, 1] - 1e-3)
+        o.set_state(qpos, np.zeros(o.nv), qpos[: o.nu])
+        gx = o.field("geom_xpos").reshape(-1, 3)
+        p = gx[pads[trial % len(pads)]]
+        ax = trial % 3
+        off = np.zeros(3)
+        off[ax] = (0.02 + 0.01 - 0.002) * (1 if trial % 2 else -1)
+        qpos[-7:-4] = p + off
+        qpos[-4:] = [1, 0, 0, 0]
+        qvel = rng.normal(size=o.nv) * 0.1
+        state = dict(qpos=qpos, qvel=qvel, ctrl=qpos[: o.nu].copy(), warm=np.zeros(o.nv), mocap=st0["mocap"][0][: 7 * o.nmocap].copy(), time=0.0)
+        o.set_state(state["qpos"], state["qvel"], state["ctrl"], state["warm"], 0.0, state["mocap"] if o.nmocap else None)
+        r, fl = o.reward(with_flags=True)
+        if not fl & 6:
+            continue
+        seen += 1
+        act = rng.uniform(-1, 1, o.task.act_dim).astype(np.float32)
+        hs.set_state(state)
+        out = hs.env_step(act)
+        assert hs.fault() == "", hs.fault()
+        o.set_state(state["qpos"], state["qvel"], state["ctrl"], state["warm"], 0.0, state["mocap"] if o.nmocap else None)
+        obs, rew = o.step(act)
+        a, b = hs.get_state(), o.get_state()
+        assert rel_err(a["qpos"], b["qpos"]) < 1e-10 and rel_err(a["qvel"], b["qvel"], floor=1.0) < 1e-9, (trial, rel_err(a["qvel"], b["qvel"]))
+        assert rel_err(out["obs"], obs, floor=1.0) < 1e-9
+    assert seen >= 4
+
+
 def test_emulator_reports_divergent_collectives():
     """The checker itself: a collective reached by only some lanes is reported, not silently executed."""
     import ctypes as C
