@@ -1126,10 +1126,10 @@ KM_TPL KM_HD void step2(KM_ARGS) {
   KM_CLK(CLK_BARRIER);
 #if KM_WARP_CODE && KM_WARP_SOLVER
   if constexpr (G == 32) {
-    // register-resident solver (km_solver_warp.cuh); it has lanes for four contacts (all the table corners, or finger
-    // pads + corners up to four) -- beyond that the generic solver takes over
-    if (e.ncon <= 4) { if (e.coupled) fwd_acc_constraint_w<S, T, true>(e, m, g); else fwd_acc_constraint_w<S, T, false>(e, m, g); }
-    else { fwd_acceleration<S, T, G>(e, m, g); fwd_constraint<S, T, G>(e, m, g); }
+    // register-resident solver (km_solver_warp.cuh); the coupled instantiation (a finger pad touches the cube) carries
+    // two contact sets (up to eight contacts) and a dense Hessian
+    if (e.coupled) fwd_acc_constraint_w<S, T, true>(e, m, g);
+    else fwd_acc_constraint_w<S, T, false>(e, m, g);
     euler<S, T, G>(e, m, g);
     KM_CLK(CLK_EULER);
     return;

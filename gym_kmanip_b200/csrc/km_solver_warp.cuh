@@ -26,7 +26,8 @@ namespace km {
 // whole CTA at the next phase barrier): dense H = M + diag + sum_c J_c^T W_c J_c over all NV dofs, assembled entry by
 // entry over the lanes, factorised one row per lane (NV pivots by shuffles), no caching.
 template <class S, typename T, class E>
-KM_DN T warp_direction_dense(E& e, const Model<S, T>& m, int lane, int dofi, bool isdof, T hd, unsigned pm, unsigned nm, int ncon, T grad) {
+KM_DN T warp_direction_dense(E& e, const Model<S, T>& m, int lane, int dofi, bool isdof, T hd, unsigned pm0, unsigned nm0, unsigned pm1,
+                             unsigned nm1, int ncon, T grad) {
 typedef Dim<S> D;
 typedef Num<T> N;
 constexpr int NV = D::NV, NVA = D::NVA, CL0 = NV <= 16 ? 16 : 0;
@@ -45,10 +46,11 @@ constexpr unsigned FULL = 0xffffffffu;
       if (((sup >> i) & 1u) && ((sup >> j) & 1u)) {
         const T Dc = e.con_D[c];
         const T ni = jc<S, T>(e, c, 0, i), nj = jc<S, T>(e, c, 0, j);
+        const unsigned pm = c < 4 ? pm0 : pm1, nm = c < 4 ? nm0 : nm1;   // contact set of c: lanes CL0 + 4 (c mod 4) + k
         T cnt = 0, acc = 0;
 #pragma unroll
         for (int k = 1; k < 4; k++) {
-          const T p = (pm >> (CL0 + 4 * c + k)) & 1u ? T(1) : T(0), q = (nm >> (CL0 + 4 * c + k)) & 1u ? T(1) : T(0);
+          const T p = (pm >> (CL0 + 4 * (c & 3) + k)) & 1u ? T(1) : T(0), q = (nm >> (CL0 + 4 * (c & 3) + k)) & 1u ? T(1) : T(0);
           const T muk = e.con_mu[c][k - 1];
           const T ti = jc<S, T>(e, c, k, i), tj = jc<S, T>(e, c, k, j);
           cnt += p + q;
@@ -105,18 +107,20 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
   static constexpr int NV = D::NV, NVA = D::NVA, BS = max_block<S>();
   static constexpr int CL0 = NV <= 16 ? 16 : 0;       // first lane of the contact role
   static constexpr bool SH = CL0 == 0;                // contact rows share lanes with dofs (extra slots)
-  static constexpr int NS = SH ? 4 : 2, EA = SH ? 2 : 0;   // row slots per lane; first slot of the pyramid-edge pair
+  // contact sets: a contact lane carries one base row of contact cc (set 0) and, in the coupled instantiation, of contact
+  // cc + 4 (set 1: finger pads + table corners can add up to eight contacts); EA + 2 s = first slot of set s's edge pair
+  static constexpr int NCS = CPL ? 2 : 1, EA = SH ? 2 : 0, NS = EA + 2 * NCS;
   static_assert(NV <= 32 && D::NFRIC <= NV, "one lane per dof");
 
   E& e;
   const Model<S, T>& m;
   const Grp<32>& g;
   // roles
-  int lane, dofi, b0, bn, li, cl, cc, cb, ncon, cslot;
-  unsigned csup;
-  bool isdof, isarm, iscube, iscon, isedge, has_f, has_l;
+  int lane, dofi, b0, bn, li, cl, cc, cb, ncon, cslot[NCS];
+  unsigned csup[NCS];
+  bool isdof, isarm, iscube, iscon[NCS], isedge[NCS], has_f, has_l;
   // row constants: slot 0 = friction-loss row of the dof (or a pyramid edge on the solo-arm contact lanes), slot 1 = limit
-  T cdiag, rf0, fl0, sg, mu, Dr[NS];
+  T cdiag, rf0, fl0, sg, mu[NCS], Dr[NS];
   // solver state
   T qacc, Ma, grad, search, Mv, qs, as, jar[NS], jv[NS], dinv, hd_cached;
   int evals;
@@ -124,7 +128,7 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
   KM_DI WarpSolver(E& e_, const Model<S, T>& m_, const Grp<32>& g_) : e(e_), m(m_), g(g_) {}
 
   KM_DI T* xs() const { return e.c.search; }   // broadcast buffer of a dof-space vector
-  KM_DI T* fbs() const { return e.c.Mv; }      // base-row forces of the contacts (16)
+  KM_DI T* fbs() const { return CPL ? e.c.efc_force : e.c.Mv; }   // base-row forces of the contacts (16 per contact set)
 
   // M x for this lane's dof (x of every dof is in xs())
   KM_DI T mulM(T xi) const {
@@ -135,20 +139,24 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
   }
   // J x for this lane's rows (cube part of x in xs())
   KM_DI void jrows(T xi, T* out) const {
-    T pb = 0;
-    const T* jr = e.Jq[iscon ? cc : 0][iscon ? cb : 0];
-#pragma unroll
-    for (int k = 0; k < 6; k++) pb += jr[k] * xs()[NVA + k];
-    pb = iscon ? pb : T(0);
-    if constexpr (CPL) {             // finger-pad contacts: arm columns of the base row (its dof support only)
-      if (iscon && cslot < D::NPAD)
-        for (int j = 0; j < NVA; j++) pb += ((csup >> j) & 1u) ? e.Ja[cslot][cb][j] * xs()[j] : T(0);
-    }
-    const T p0 = __shfl_sync(0xffffffffu, pb, lane & ~3);
     out[0] = has_f ? xi : T(0);
     out[1] = has_l ? sg * xi : T(0);
-    if (SH) { out[EA] = isedge ? p0 + mu * pb : T(0); out[EA + 1] = isedge ? p0 - mu * pb : T(0); }
-    else if (isedge) { out[0] = p0 + mu * pb; out[1] = p0 - mu * pb; }
+    sfor<0, NCS>([&](auto Cs) {
+      constexpr int cs = decltype(Cs)::value;
+      T pb = 0;
+      const T* jr = e.Jq[iscon[cs] ? cc + 4 * cs : 0][iscon[cs] ? cb : 0];
+#pragma unroll
+      for (int k = 0; k < 6; k++) pb += jr[k] * xs()[NVA + k];
+      pb = iscon[cs] ? pb : T(0);
+      if constexpr (CPL) {             // finger-pad contacts: arm columns of the base row (its dof support only)
+        if (iscon[cs] && cslot[cs] < D::NPAD)
+          for (int j = 0; j < NVA; j++) pb += ((csup[cs] >> j) & 1u) ? e.Ja[cslot[cs]][cb][j] * xs()[j] : T(0);
+      }
+      const T p0 = __shfl_sync(0xffffffffu, pb, lane & ~3);
+      constexpr int ea = EA + 2 * cs;
+      if (SH || cs > 0) { out[ea] = isedge[cs] ? p0 + mu[cs] * pb : T(0); out[ea + 1] = isedge[cs] ? p0 - mu[cs] * pb : T(0); }
+      else if (isedge[cs]) { out[0] = p0 + mu[cs] * pb; out[1] = p0 - mu[cs] * pb; }
+    });
   }
   // cost and force of slot s at residual x
   template <int s> KM_DI T rowcost(T x, T* f) const {
@@ -172,11 +180,14 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
     T c = 0, f[NS];
     sfor<0, NS>([&](auto Sx) { constexpr int s = decltype(Sx)::value; c += rowcost<s>(jar[s], &f[s]); });
     T qfc = (SH || isdof) ? f[0] + sg * f[1] : T(0);
-    const T fp = isedge ? f[EA] : T(0), fn = isedge ? f[EA + 1] : T(0);
-    T sn = fp + fn;
-    sn += __shfl_xor_sync(0xffffffffu, sn, 1);
-    sn += __shfl_xor_sync(0xffffffffu, sn, 2);
-    if (cl >= 0 && cl < 16) fbs()[cl] = iscon ? (cb == 0 ? sn : mu * (fp - fn)) : T(0);
+    sfor<0, NCS>([&](auto Cs) {
+      constexpr int cs = decltype(Cs)::value;
+      const T fp = isedge[cs] ? f[EA + 2 * cs] : T(0), fn = isedge[cs] ? f[EA + 2 * cs + 1] : T(0);
+      T sn = fp + fn;
+      sn += __shfl_xor_sync(0xffffffffu, sn, 1);
+      sn += __shfl_xor_sync(0xffffffffu, sn, 2);
+      if (cl >= 0 && cl < 16) fbs()[16 * cs + cl] = iscon[cs] ? (cb == 0 ? sn : mu[cs] * (fp - fn)) : T(0);
+    });
     g.sync();
     if (iscube)
       for (int c2 = 0; c2 < ncon; c2++)
@@ -281,9 +292,13 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
     const bool q0 = has_f ? (jar[0] > -rf0 && jar[0] < rf0) : (jar[0] < T(0));
     const bool q1 = jar[1] < T(0);
     const T hd = ((has_f && q0) ? Dr[0] : T(0)) + ((has_l && q1) ? Dr[1] : T(0));
-    const unsigned pm = __ballot_sync(FULL, isedge && (SH ? jar[EA] < T(0) : q0));
-    const unsigned nm = __ballot_sync(FULL, isedge && (SH ? jar[EA + 1] < T(0) : q1));
-    if constexpr (CPL) { search = warp_direction_dense<S, T>(e, m, lane, dofi, isdof, hd, pm, nm, ncon, grad); return; }
+    const unsigned pm = __ballot_sync(FULL, isedge[0] && (SH ? jar[EA] < T(0) : q0));
+    const unsigned nm = __ballot_sync(FULL, isedge[0] && (SH ? jar[EA + 1] < T(0) : q1));
+    if constexpr (CPL) {
+      const unsigned pm1 = __ballot_sync(FULL, isedge[1] && jar[EA + 2] < T(0)), nm1 = __ballot_sync(FULL, isedge[1] && jar[EA + 3] < T(0));
+      search = warp_direction_dense<S, T>(e, m, lane, dofi, isdof, hd, pm, nm, pm1, nm1, ncon, grad);
+      return;
+    }
     const bool refactor = __any_sync(FULL, isarm && hd != hd_cached);
     // The cube block depends on the states of the pyramid rows (pm, nm) and of the cube's friction-loss rows only: when
     // none of them changed since the previous iteration (the usual case once the active set has settled) its factor in
@@ -419,10 +434,13 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
     b0 = m.blk0[dofi]; bn = m.blkn[dofi]; li = dofi - b0;
     ncon = e.ncon;
     cl = lane - CL0; cc = (cl >> 2) & 3; cb = cl & 3;
-    iscon = cl >= 0 && cl < 16 && cc < ncon;
-    cslot = (CPL && iscon) ? e.con_slot[cc] : D::NPAD;
-    csup = (CPL && iscon) ? e.con_sup[cc] : 0u;
-    isedge = iscon && cb > 0;
+    sfor<0, NCS>([&](auto Cs) {
+      constexpr int cs = decltype(Cs)::value;
+      iscon[cs] = cl >= 0 && cl < 16 && cc + 4 * cs < ncon;
+      cslot[cs] = (CPL && iscon[cs]) ? e.con_slot[cc + 4 * cs] : D::NPAD;
+      csup[cs] = (CPL && iscon[cs]) ? e.con_sup[cc + 4 * cs] : 0u;
+      isedge[cs] = iscon[cs] && cb > 0;
+    });
     const int base = D::NFRIC + e.nlim;
     cdiag = iscube ? (li < 3 ? m.cube_mass : m.cube_inertia[li < 3 ? 0 : li - 3]) : T(0);
     // rows of this lane
@@ -434,13 +452,16 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
     if (has_f) { Dr[0] = m.fr_D[fr]; ar[0] = e.efc_aref[fr]; }
     sg = T(1);
     if (has_l) { Dr[1] = e.efc_D[lr]; ar[1] = e.efc_aref[lr]; sg = efc_neg(e.efc_desc[lr]) ? T(-1) : T(1); }
-    mu = 0;
-    if (isedge) {
-      const int rp = base + 6 * cc + 2 * (cb - 1);
-      mu = e.con_mu[cc][cb - 1];
-      Dr[EA] = e.con_D[cc]; Dr[EA + 1] = Dr[EA];
-      ar[EA] = e.efc_aref[rp]; ar[EA + 1] = e.efc_aref[rp + 1];
-    }
+    sfor<0, NCS>([&](auto Cs) {
+      constexpr int cs = decltype(Cs)::value;
+      mu[cs] = 0;
+      if (isedge[cs]) {
+        const int c = cc + 4 * cs, rp = base + 6 * c + 2 * (cb - 1);
+        mu[cs] = e.con_mu[c][cb - 1];
+        Dr[EA + 2 * cs] = e.con_D[c]; Dr[EA + 2 * cs + 1] = e.con_D[c];
+        ar[EA + 2 * cs] = e.efc_aref[rp]; ar[EA + 2 * cs + 1] = e.efc_aref[rp + 1];
+      }
+    });
     evals = 0;
     qs = isdof ? e.qfrc_smooth[dofi] : T(0);
     // ---- smooth acceleration: factor M (every block), qacc_smooth = M^{-1} qfrc_smooth
