@@ -22,83 +22,6 @@ namespace km {
 #if defined(__CUDACC__) || defined(KM_WARP_EMU)
 
 
-// Coupled case (a finger pad touches the cube, well under 1 % of the env-steps -- but an env on the slow path stalls its
-// whole CTA at the next phase barrier): dense H = M + diag + sum_c J_c^T W_c J_c over all NV dofs, assembled entry by
-// entry over the lanes, factorised one row per lane (NV pivots by shuffles), no caching.
-template <class S, typename T, class E>
-KM_DN T warp_direction_dense(E& e, const Model<S, T>& m, int lane, int dofi, bool isdof, T hd, unsigned pm0, unsigned nm0, unsigned pm1,
-                             unsigned nm1, int ncon, T grad) {
-typedef Dim<S> D;
-typedef Num<T> N;
-constexpr int NV = D::NV, NVA = D::NVA, CL0 = NV <= 16 ? 16 : 0;
-constexpr unsigned FULL = 0xffffffffu;
-  T* hds = e.c.hdiag;
-  if (isdof) hds[lane] = hd;
-  __syncwarp(FULL);
-  for (int w = lane; w < NV * (NV + 1) / 2; w += 32) {
-    const int ij = m.pair_ij[w], i = ij >> 8, j = ij & 255;
-    T h;
-    if (i < NVA) h = e.M[i][j];
-    else h = i == j ? (i - NVA < 3 ? m.cube_mass : m.cube_inertia[i - NVA < 3 ? 0 : i - NVA - 3]) : T(0);
-    if (i == j) h += hds[i];
-    for (int c = 0; c < ncon; c++) {
-      const unsigned sup = e.con_sup[c];
-      if (((sup >> i) & 1u) && ((sup >> j) & 1u)) {
-        const T Dc = e.con_D[c];
-        const T ni = jc<S, T>(e, c, 0, i), nj = jc<S, T>(e, c, 0, j);
-        const unsigned pm = c < 4 ? pm0 : pm1, nm = c < 4 ? nm0 : nm1;   // contact set of c: lanes CL0 + 4 (c mod 4) + k
-        T cnt = 0, acc = 0;
-#pragma unroll
-        for (int k = 1; k < 4; k++) {
-          const T p = (pm >> (CL0 + 4 * (c & 3) + k)) & 1u ? T(1) : T(0), q = (nm >> (CL0 + 4 * (c & 3) + k)) & 1u ? T(1) : T(0);
-          const T muk = e.con_mu[c][k - 1];
-          const T ti = jc<S, T>(e, c, k, i), tj = jc<S, T>(e, c, k, j);
-          cnt += p + q;
-          acc += Dc * muk * (p - q) * (ni * tj + ti * nj) + Dc * muk * muk * (p + q) * ti * tj;
-        }
-        h += Dc * cnt * ni * nj + acc;
-      }
-    }
-    e.c.H[i][j] = h;
-    e.c.H[j][i] = h;
-  }
-  __syncwarp(FULL);
-  T row[NV], di = 1;
-  sfor<0, NV>([&](auto J) { constexpr int j = decltype(J)::value; row[j] = e.c.H[dofi][j]; });
-  __syncwarp(FULL);
-  sfor<0, NV>([&](auto J) {
-    constexpr int j = decltype(J)::value;
-    const T ajj = __shfl_sync(FULL, row[j], j);
-    const T inv = N::rsqrt(tmax(ajj, N::minval()));
-    const T lij = row[j] * inv;
-    row[j] = lij;
-    di = dofi == j ? inv : di;
-    sfor<j + 1, NV>([&](auto K) {
-      constexpr int k = decltype(K)::value;
-      row[k] -= lij * __shfl_sync(FULL, lij, k);
-    });
-  });
-  sfor<0, NV>([&](auto J) { constexpr int j = decltype(J)::value; if (isdof && j <= dofi) e.c.H[dofi][j] = row[j]; });
-  __syncwarp(FULL);
-  T acc = grad, y = 0;
-  sfor<0, NV>([&](auto J) {
-    constexpr int j = decltype(J)::value;
-    const T yj = __shfl_sync(FULL, acc * di, j);
-    y = dofi == j ? yj : y;
-    acc = dofi > j ? acc - row[j] * yj : acc;
-  });
-  T acc2 = y, x = 0;
-  sfor_rev<NV>([&](auto J) {
-    constexpr int j = decltype(J)::value;
-    const T xj = __shfl_sync(FULL, acc2 * di, j);
-    x = dofi == j ? xj : x;
-    const T l = e.c.H[j][dofi];
-    acc2 = j > dofi ? acc2 - l * xj : acc2;
-  });
-  return isdof ? -x : T(0);
-}
-
-
 // CPL: the instantiation for envs whose cube touches a finger pad (pad contacts carry arm columns, H is dense).  It is a
 // separate instantiation so that the common one carries none of its state or code (28 warps per SM: 72 registers).
 template <class S, typename T, class E, bool CPL> struct WarpSolver {
@@ -287,6 +210,96 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
     g.sync();
   }
 
+  // Coupled case (a finger pad touches the cube, well under 1 % of the env-steps -- but the kernel ends with its slowest
+  // env, and that is a coupled one): dense H = M + diag + sum_c J_c^T W_c J_c over all NV dofs.  One row per lane: for
+  // every contact the lane forms u = W_c J_c[:, i] from its own column of the base rows (W_c is the 4 x 4 arrow-head of
+  // the active pyramid edges) and adds u . J_c[:, j] for the columns j of the contact's support (broadcast loads);
+  // table-corner contacts only touch the cube block.  The factor stays in e.c.H / dinv and, like the block factors of
+  // the common case, is reused while the active set (hd, pm, nm of both contact sets) is unchanged.
+  KM_DI void dense_factor(T hd, unsigned pm0, unsigned nm0, unsigned pm1, unsigned nm1) {
+    T row[NV];
+    sfor<0, NV>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      T v = 0;
+      if constexpr (j < NVA) v = isarm ? e.M[isarm ? dofi : 0][j] : T(0);
+      row[j] = j == dofi ? v + hd + cdiag : v;
+    });
+    for (int c = 0; c < ncon; c++) {   // warp-uniform
+      const int slot = e.con_slot[c];
+      const unsigned sup = e.con_sup[c];
+      const bool pad = slot < D::NPAD;
+      const bool in = isdof && ((sup >> dofi) & 1u);
+      const int sa = pad ? slot : 0;
+      T own[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const T v = iscube ? e.Jq[c][b][iscube ? li : 0] : e.Ja[sa][b][isarm ? dofi : 0];
+        own[b] = in ? v : T(0);
+      }
+      const unsigned pmc = c < 4 ? pm0 : pm1, nmc = c < 4 ? nm0 : nm1;   // contact set of c: lanes CL0 + 4 (c mod 4) + k
+      const int sh = CL0 + 4 * (c & 3);
+      const T Dc = e.con_D[c];
+      T cnt = 0, u[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 1; k < 4; k++) {
+        const T p = (pmc >> (sh + k)) & 1u ? T(1) : T(0), q = (nmc >> (sh + k)) & 1u ? T(1) : T(0);
+        const T muk = e.con_mu[c][k - 1];
+        const T w0 = Dc * muk * (p - q), wk = Dc * muk * muk * (p + q);
+        cnt += p + q;
+        u[0] += w0 * own[k];
+        u[k] = w0 * own[0] + wk * own[k];
+      }
+      u[0] += Dc * cnt * own[0];
+      if (pad) {
+        sfor<0, NVA>([&](auto J) {
+          constexpr int j = decltype(J)::value;
+          if ((sup >> j) & 1u) row[j] += u[0] * e.Ja[sa][0][j] + u[1] * e.Ja[sa][1][j] + u[2] * e.Ja[sa][2][j] + u[3] * e.Ja[sa][3][j];
+        });
+      }
+      sfor<NVA, NV>([&](auto J) {
+        constexpr int j = decltype(J)::value, k = j - NVA;
+        row[j] += u[0] * e.Jq[c][0][k] + u[1] * e.Jq[c][1][k] + u[2] * e.Jq[c][2][k] + u[3] * e.Jq[c][3][k];
+      });
+    }
+    T di = 1;
+    sfor<0, NV>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const T ajj = __shfl_sync(FULL, row[j], j);
+      const T inv = N::rsqrt(tmax(ajj, N::minval()));
+      const T lij = row[j] * inv;
+      row[j] = lij;
+      di = dofi == j ? inv : di;
+      sfor<j + 1, NV>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        row[k] -= lij * __shfl_sync(FULL, lij, k);
+      });
+    });
+    dinv = di;
+    sfor<0, NV>([&](auto J) { constexpr int j = decltype(J)::value; if (isdof && j <= dofi) e.c.H[dofi][j] = row[j]; });
+    g.sync();
+  }
+  // x = H^{-1} rhs with the dense factor in e.c.H (row i: L[i][j], j < i; column i: L[j][i], j > i) and dinv
+  KM_DI T dense_solve(T rhs) const {
+    const T* hrow = e.c.H[dofi];
+    T acc = rhs, y = 0;
+    sfor<0, NV>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const T yj = __shfl_sync(FULL, acc * dinv, j);
+      y = dofi == j ? yj : y;
+      const T l = hrow[j];
+      acc = dofi > j ? acc - l * yj : acc;
+    });
+    T acc2 = y, x = 0;
+    sfor_rev<NV>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const T xj = __shfl_sync(FULL, acc2 * dinv, j);
+      x = dofi == j ? xj : x;
+      const T l = e.c.H[j][dofi];
+      acc2 = j > dofi ? acc2 - l * xj : acc2;
+    });
+    return x;
+  }
+
   // Newton direction: search = -H^{-1} grad
   KM_DI void direction() {
     const bool q0 = has_f ? (jar[0] > -rf0 && jar[0] < rf0) : (jar[0] < T(0));
@@ -296,7 +309,16 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
     const unsigned nm = __ballot_sync(FULL, isedge[0] && (SH ? jar[EA + 1] < T(0) : q1));
     if constexpr (CPL) {
       const unsigned pm1 = __ballot_sync(FULL, isedge[1] && jar[EA + 2] < T(0)), nm1 = __ballot_sync(FULL, isedge[1] && jar[EA + 3] < T(0));
-      search = warp_direction_dense<S, T>(e, m, lane, dofi, isdof, hd, pm, nm, pm1, nm1, ncon, grad);
+      int* key = e.c.efc_state;
+      const bool rebuild = __any_sync(FULL, (isdof && hd != hd_cached) || (unsigned)key[0] != pm || (unsigned)key[1] != nm ||
+                                                (unsigned)key[2] != pm1 || (unsigned)key[3] != nm1);
+      if (rebuild) {
+        g.sync();
+        if (lane == 0) { key[0] = (int)pm; key[1] = (int)nm; key[2] = (int)pm1; key[3] = (int)nm1; }
+        hd_cached = hd;
+        dense_factor(hd, pm, nm, pm1, nm1);
+      }
+      { const T x = dense_solve(grad); search = isdof ? -x : T(0); }   // every lane takes part in the shuffles
       return;
     }
     const bool refactor = __any_sync(FULL, isarm && hd != hd_cached);

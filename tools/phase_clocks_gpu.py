@@ -21,9 +21,23 @@ names = ["kin", "crb", "coll+mkc", "vel", "acc", "sol_setup", "sol_dir", "sol_ls
 for t in range(40):
     act = torch.rand(n, sim.act_dim, device="cuda", generator=gen) * 2 - 1
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); sim.step(act, contacts=False); e1.record(); torch.cuda.synchronize()
+    e0.record(); sim.step(act, contacts=True); e1.record(); torch.cuda.synchronize()
     if t in (3, 8, 15, 30, 39):
         c = clk.cpu().double()
         tot = c.sum(1)
         print(f"step {t}: {e0.elapsed_time(e1):.3f} ms; cycles per env step (lane 0 of each env): mean total {tot.mean():.0f} max {tot.max():.0f}")
         print("   " + "  ".join(f"{nm} {c[:, i].mean() / tot.mean() * 100:.1f}%" for i, nm in enumerate(names)))
+        # per-CTA view (envs of a CTA march in phase, so their totals agree): which CTAs set the kernel time, and why
+        epb_ = sim.launch_config()["envs_per_block"]
+        ncta = (n + epb_ - 1) // epb_
+        pad = ncta * epb_ - n
+        tp = torch.cat([tot, tot.new_zeros(pad)]).view(ncta, epb_).max(1).values
+        q = torch.quantile(tp, torch.tensor([0.1, 0.5, 0.9, 0.99, 1.0], dtype=tp.dtype))
+        print("   per-CTA total cycles p10/p50/p90/p99/max: " + " ".join(f"{x:.0f}" for x in q.tolist()))
+        busy = c[:, :11].sum(1) + c[:, 12] + c[:, 13]          # everything but the barrier waits
+        bq = torch.quantile(busy, torch.tensor([0.1, 0.5, 0.9, 0.99, 1.0], dtype=tp.dtype))
+        print("   per-env busy cycles (no barrier waits) p10/p50/p90/p99/max: " + " ".join(f"{x:.0f}" for x in bq.tolist()))
+        top = torch.argsort(busy, descending=True)[:6]
+        fl = sim.con_flags.cpu(); nc = sim.ncon.cpu()
+        for i in top.tolist():
+            print(f"     env {i} (cta {i // epb_}) busy {busy[i]:.0f} ncon {int(nc[i])} flags {int(fl[i])} | " + " ".join(f"{nm} {c[i, k]:.0f}" for k, nm in enumerate(names)))
