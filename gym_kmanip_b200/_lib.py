@@ -15,7 +15,7 @@ _LIB = None
 
 EXPORTS = [
     "km_last_error", "km_version", "km_measure_fma_peak", "km_create", "km_destroy", "km_nq", "km_nv", "km_nu", "km_nmocap", "km_obs_dim",
-    "km_act_dim", "km_state_dim", "km_max_contacts", "km_num_envs", "km_dtype", "km_configure", "km_launch_count",
+    "km_act_dim", "km_state_dim", "km_max_contacts", "km_num_envs", "km_dtype", "km_configure", "km_set_env_ordering", "km_launch_count",
     "km_launch_config", "km_reset", "km_step", "km_get_state", "km_set_state", "km_state_ptr", "km_contacts",
     "km_solver_stats", "km_episode_stats", "km_set_host_stream", "km_debug_phase_clocks", "km_site_poses", "km_n_arm", "km_reset_host", "km_step_host",
     "km_render", "km_render_host", "km_render_record_floats", "km_get_render_records",
@@ -58,6 +58,7 @@ def load() -> C.CDLL:
               "km_num_envs", "km_dtype"):
         getattr(L, n).argtypes = [vp]
     L.km_configure.argtypes = [vp, ip, ip]
+    L.km_set_env_ordering.argtypes = [vp, ip]
     L.km_launch_count.argtypes = [vp]
     L.km_launch_count.restype = C.c_longlong
     L.km_launch_config.argtypes = [vp] + [C.POINTER(ip)] * 5

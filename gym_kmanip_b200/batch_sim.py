@@ -94,6 +94,10 @@ class BatchSim:
         _lib.check(self.L.km_configure(self.h, lanes_per_env, envs_per_block))
         return self.launch_config()
 
+    def set_env_ordering(self, mode: int = -1):
+        """Cost-ordered walk of the step kernel (km_set_env_ordering): -1 automatic, 0 off, 1 on.  Results do not depend on it."""
+        _lib.check(self.L.km_set_env_ordering(self.h, int(mode)))
+
     def launch_config(self) -> Dict[str, int]:
         v = [C.c_int(0) for _ in range(5)]
         _lib.check(self.L.km_launch_config(self.h, *[C.byref(x) for x in v]))

@@ -31,6 +31,8 @@ struct km_sim {
   void* d_model;
   void* d_state;
   int *d_step, *d_episode, *d_niter, *d_ls;
+  int *d_order, *d_tile_counter;   // cost-ordered walk of the step kernels (order_envs)
+  int order_mode;   // -1 = automatic (on when the lane-group mapping walks more tiles than CTAs), 0 = off, 1 = on
   unsigned* d_clk;   // caller-owned buffer of km_debug_phase_clocks (debug builds)
   void* d_ep_return;  // running return of every env (dtype of the handle)
   double* d_totals;   // rollout totals {sum reward, env steps, finished episodes, success steps}
@@ -91,7 +93,7 @@ static int configure(km_sim* h, int G, int epb) {
     const int threads = (epb + h->lpw - 1) / h->lpw * 32;
     if (epb < 1 || threads > 512) return fail(KM_ERR_ARG, "envs_per_block out of range for thread-per-env (local) CTAs");
     int ctas = 0;
-    KM_CUDA(h->vt.prepare(2, threads, &ctas));
+    KM_CUDA(h->vt.prepare(2, threads, 0, &ctas));
     if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
     // one CTA per SM by default: the records of the resident envs (6.9 KB each for the solo arm) should stay in L2
     ctas = h->tpl_ctas;
@@ -110,7 +112,7 @@ static int configure(km_sim* h, int G, int epb) {
     }
     if (epb < 1 || epb > cap) return fail(KM_ERR_ARG, "envs_per_block out of range for thread-per-env CTAs");
     int ctas = 0;
-    KM_CUDA(h->vt.prepare(1, epb, &ctas));
+    KM_CUDA(h->vt.prepare(1, epb, 0, &ctas));
     if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
     h->G = 1; h->epb = epb; h->ctas_per_sm = ctas;
     const long tiles = ((long)h->n + epb - 1) / epb, resident = (long)h->num_sms * ctas;
@@ -122,7 +124,9 @@ static int configure(km_sim* h, int G, int epb) {
   KM_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   dev_smem -= (int)km::KM_SMEM_STATIC;   // the kernels' static shared memory (CTA totals) comes out of the same budget
   const size_t model_b = (h->vt.model_bytes + 15) / 16 * 16;
-  const int fit = (int)(((size_t)dev_smem - model_b) / h->vt.env_bytes);
+  // the exact-parity IK keeps its work arrays in shared memory behind the env records (km_ik_trf.cuh)
+  const size_t env_b = h->vt.env_bytes + (h->ik_mode == 1 ? sizeof(km::trf::TrfWork) : 0);
+  const int fit = (int)(((size_t)dev_smem - model_b) / env_b);
   const int cap = fit * G > h->vt.max_threads ? h->vt.max_threads / G : fit;
   if (epb == 0) {
     // default: fill the shared memory of every SM with envs, shrunk so that the waves are balanced (4096 envs on 148 SMs
@@ -136,10 +140,10 @@ static int configure(km_sim* h, int G, int epb) {
     epb = per_sm >= 16 ? (per_sm + 1) / 2 : per_sm;
   }
   if (epb < 1 || epb > cap) return fail(KM_ERR_ARG, "envs_per_block out of range for this scene / precision");
-  if (model_b + (size_t)epb * h->vt.env_bytes > (size_t)dev_smem)
+  if (model_b + (size_t)epb * env_b > (size_t)dev_smem)
     return fail(KM_ERR_ARG, "envs_per_block needs more shared memory than a CTA can opt in to");
   int ctas = 0;
-  KM_CUDA(h->vt.prepare(G, epb, &ctas));
+  KM_CUDA(h->vt.prepare(G, epb, (int)(env_b - h->vt.env_bytes), &ctas));
   if (ctas < 1) return fail(KM_ERR_CUDA, "kernel does not fit on an SM with this configuration");
   h->G = G; h->epb = epb; h->ctas_per_sm = ctas;
   const long tiles = ((long)h->n + epb - 1) / epb;
@@ -155,6 +159,7 @@ static KmArgs base_args(km_sim* h, void* stream) {
   a.niter = h->d_niter; a.ls = h->d_ls; a.clk = h->d_clk;
   a.ep_return = h->d_ep_return; a.totals = h->d_totals;
   a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid; a.lpw = h->lpw > 0 ? h->lpw : 32; a.tpl_small_regs = h->tpl_ctas > 1;
+  a.trf_bytes = h->ik_mode == 1 ? (int)sizeof(km::trf::TrfWork) : 0;
   a.stream = (cudaStream_t)stream;
   return a;
 }
@@ -195,6 +200,36 @@ template <typename T> static int measure_fma(int device, double* tflops) {
   KM_CUDA(cudaGetLastError());
   *tflops = best;
   return KM_OK;
+}
+
+// Cost-ordered walk.  The step kernels march the envs of a CTA (warp-per-env mapping) or of a warp (thread-per-env
+// mapping) in lockstep, so a tile costs what its slowest env costs -- and the cost of an env (Newton iterations, line-search
+// evaluations: contact state) persists from one step to the next.  Before every step the envs are therefore bucketed by
+// the line-search evaluations of their previous step (counting sort, 256 buckets, most expensive first): tiles become
+// homogeneous, and the CTAs fetch them dynamically, longest first.  One CTA: the batch is at most a few 100 000 envs.
+__global__ void __launch_bounds__(1024) k_order_envs(const int* __restrict__ cost, int n, int shift, int* __restrict__ order, int* tile_counter) {
+  __shared__ int hist[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = cost[i] >> shift;
+    atomicAdd(&hist[255 - (c > 255 ? 255 : c)], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {   // exclusive scan of the 256 counts by one warp (8 per lane)
+    int v[8], s = 0;
+    for (int k = 0; k < 8; k++) { v[k] = hist[threadIdx.x * 8 + k]; s += v[k]; }
+    int incl = s;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+    int run = incl - s;
+    for (int k = 0; k < 8; k++) { hist[threadIdx.x * 8 + k] = run; run += v[k]; }
+    if (threadIdx.x == 0) *tile_counter = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = cost[i] >> shift;
+    order[atomicAdd(&hist[255 - (c > 255 ? 255 : c)], 1)] = i;
+  }
 }
 
 extern "C" {
@@ -244,6 +279,8 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   KM_ALLOC(h->d_episode, n * sizeof(int));
   KM_ALLOC(h->d_niter, n * sizeof(int));
   KM_ALLOC(h->d_ls, n * sizeof(int));
+  KM_ALLOC(h->d_order, n * sizeof(int));
+  KM_ALLOC(h->d_tile_counter, sizeof(int));
   KM_ALLOC(h->d_act, n * task->act_dim * sizeof(float));
   KM_ALLOC(h->d_obs, n * h->vt.obs_dim * sb);
   KM_ALLOC(h->d_reward, n * sb);
@@ -282,6 +319,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
     rc = configure(h, 32, 0);
   }
   if (rc != KM_OK) { km_destroy(h); return rc; }
+  { const char* ev = std::getenv("KM_ORDER"); h->order_mode = ev ? std::atoi(ev) : -1; }   // experiment knob; km_set_env_ordering
   *out = h;
   return KM_OK;
 }
@@ -290,7 +328,7 @@ void km_destroy(km_handle h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   void* ptrs[] = {h->d_model, h->d_state, h->d_step, h->d_episode, h->d_niter, h->d_ls, h->d_act, h->d_obs, h->d_reward,
-                  h->d_xyz, h->d_trunc, h->d_mask, h->d_recs, h->d_rgb, h->d_ep_return, h->d_totals};
+                  h->d_xyz, h->d_trunc, h->d_mask, h->d_recs, h->d_rgb, h->d_ep_return, h->d_totals, h->d_order, h->d_tile_counter};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -314,6 +352,12 @@ int km_configure(km_handle h, int lanes_per_env, int envs_per_block) {
   return configure(h, lanes_per_env, envs_per_block);
 }
 
+int km_set_env_ordering(km_handle h, int mode) {
+  if (!h || mode < -1 || mode > 1) return fail(KM_ERR_ARG, "km_set_env_ordering: mode must be -1 (automatic), 0 or 1");
+  h->order_mode = mode;
+  return KM_OK;
+}
+
 int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* grid, int* ctas_per_sm, int* smem_bytes) {
   if (!h) return fail(KM_ERR_ARG, "null handle");
   if (lanes_per_env) *lanes_per_env = h->G;
@@ -321,7 +365,7 @@ int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* 
   if (grid) *grid = h->grid;
   if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
   if (smem_bytes)   // the local-memory mapping (G == 2) keeps only the model tables in shared memory
-    *smem_bytes = (int)((h->vt.model_bytes + 15) / 16 * 16 + (h->G == 2 ? 0 : (size_t)h->epb * (h->G == 1 ? h->vt.tpe_env_bytes : h->vt.env_bytes)));
+    *smem_bytes = (int)((h->vt.model_bytes + 15) / 16 * 16 + (h->G == 2 ? 0 : (size_t)h->epb * (h->G == 1 ? h->vt.tpe_env_bytes : h->vt.env_bytes + (h->ik_mode == 1 ? sizeof(km::trf::TrfWork) : 0))));
   return KM_OK;
 }
 
@@ -345,6 +389,13 @@ int km_step(km_handle h, const float* action_dev, const km_step_out* out, int au
     a.con_flags = out->con_flags; a.ncon = out->ncon; a.con_geoms = out->con_geoms;
     a.is_success = out->is_success; a.episode_return = out->episode_return; a.final_return = out->final_return;
     a.sim_time = out->sim_time; a.step_out = out->step_count; a.episode_out = out->episode;
+  }
+  const long tiles_ = ((long)h->n + h->epb - 1) / h->epb;
+  if (h->order_mode == 1 || (h->order_mode < 0 && h->G >= 16 && tiles_ > h->grid)) {
+    k_order_envs<<<1, 1024, 0, a.stream>>>(h->d_ls, h->n, 1, h->d_order, h->d_tile_counter);
+    KM_CUDA(cudaGetLastError());
+    a.order = h->d_order; a.tile_counter = h->d_tile_counter;
+    h->launches++;
   }
   KM_CUDA(h->vt.step(a));
   h->launches++;

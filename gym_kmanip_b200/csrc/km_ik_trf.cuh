@@ -16,7 +16,7 @@
 // and for which s * (U^T f_aug) = V^T g_h.
 // Parity against the real scipy is checked by tests/test_ik_trf.py (host build of this file, fp64) and on the GPU.
 //
-// Everything is fp64 and serial: one lane runs it (n <= 8 unknowns); it is the parity mode, not the fast path
+// Everything is fp64 and serial: one lane runs it (n <= 8 unknowns) on work arrays in shared memory; it is the parity mode, not the fast path
 // (km_task.ik_mode = 1; the default mode 0 is the fixed-iteration projected LM of km_sim.cuh).
 #pragma once
 
@@ -26,6 +26,19 @@ namespace trf {
 constexpr int NMAX = 8;
 constexpr double EPS = 2.220446049250313e-16;
 constexpr double INF = __builtin_huge_val();
+
+// Work arrays of one TRF solve.  On the device they live in the CTA's dynamic shared memory behind the env records
+// (km_launch.cuh adds sizeof(TrfWork) per env when the handle runs ik_mode = 1): as locals of the one lane that runs the
+// solve they are a 5 KB stack frame in local memory that thrashes the small L1 left beside the shared-memory carve-out,
+// and every access goes to L2.
+struct TrfWork {
+  double x[NMAX], f[6 + 2 * NMAX], g[NMAX], JtJ[NMAX][NMAX], x0n[NMAX];
+  double v[NMAX], dv[NMAX], d[NMAX], diag_h[NMAX], g_h[NMAX], Bh[NMAX][NMAX], Aw[NMAX][NMAX], V[NMAX][NMAX], w[NMAX], s[NMAX], suf[NMAX], t0[NMAX];
+  double p_gn[NMAX], Lc[NMAX][NMAX], x_new[NMAX], f_new[6 + 2 * NMAX];
+  double p_h[NMAX], p[NMAX], step[NMAX], step_h[NMAX], xp[NMAX], r_h[NMAX], r[NMAX], x_on_bound[NMAX], ag_h[NMAX], ag[NMAX];
+  double steps[NMAX], t[NMAX];
+  int hits[NMAX];
+};
 
 KM_HD double norm(const double* x, int n) {
   double s = 0;
@@ -60,8 +73,8 @@ KM_HD bool in_bounds(const double* x, const double* lb, const double* ub, int n)
 }
 // common.py: step_size_to_bound -- min over components of the step to the bound it moves towards; hits[i] = sign(s_i)
 // where that minimum is attained
-KM_HD double step_size_to_bound(const double* x, const double* s, const double* lb, const double* ub, int n, int* hits) {
-  double steps[NMAX], mn = INF;
+KM_HD double step_size_to_bound(const double* x, const double* s, const double* lb, const double* ub, int n, int* hits, double* steps) {
+  double mn = INF;
   for (int i = 0; i < n; i++) {
     steps[i] = INF;
     if (s[i] != 0.0) {
@@ -154,10 +167,9 @@ KM_HD void eig_sym(double (*A)[NMAX], int n, double* w, double (*V)[NMAX]) {
 }
 // common.py: solve_lsq_trust_region with s = singular values, suf = s * uf (= V^T g_h), V; m = number of residuals
 KM_HD void solve_lsq_trust_region(int n, int mres, const double* suf, const double* s, const double (*V)[NMAX], double Delta,
-                                  double* alpha_io, double* p) {
+                                  double* alpha_io, double* p, double* t) {
   bool full_rank = false;
   if (mres >= n) full_rank = s[n - 1] > EPS * mres * s[0];
-  double t[NMAX];
   if (full_rank) {
     for (int i = 0; i < n; i++) t[i] = suf[i] / (s[i] * s[i]);
     for (int i = 0; i < n; i++) { double r = 0; for (int j = 0; j < n; j++) r += V[i][j] * t[j]; p[i] = -r; }
@@ -203,7 +215,7 @@ KM_HD void solve_lsq_trust_region(int n, int mres, const double* suf, const doub
 // reference ik() with the restated scipy TRF.  In: b.x = x0 (current masked joints), b.qprev, b.lo, b.hi, b.goal.
 // Out: b.x = result.x, b.xn = the last point the residual / Jacobian were evaluated at (where the reference leaves
 // qpos[mask]).  Serial: call from one lane.
-template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, B& b, const Model<S, T>& m, int a) {
+template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, B& b, const Model<S, T>& m, int a, trf::TrfWork& wk) {
   using namespace trf;
   typedef Num<double> N;
   Grp<1> g1;
@@ -213,7 +225,7 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
   const int max_nfev = 100 * n;
   const double* lb = b.lo;
   const double* ub = b.hi;
-  double x[NMAX], f[6 + 2 * NMAX], g[NMAX], JtJ[NMAX][NMAX];
+  double (&x)[NMAX] = wk.x, (&f)[6 + 2 * NMAX] = wk.f, (&g)[NMAX] = wk.g, (&JtJ)[NMAX][NMAX] = wk.JtJ;
   auto eval_f = [&](const double* xx, double* ff) {
     ik_chain_fk<S, T, 1>(e, b, m, a, xx);
     ik_residual<S, T, 1>(e, b, m, g1, a, xx, ff);
@@ -236,15 +248,16 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
   };
   for (int i = 0; i < n; i++) x[i] = b.x[i];
   make_strictly_feasible(x, lb, ub, n, 1e-10);           // least_squares.py
-  double x0n[NMAX];
+  double (&x0n)[NMAX] = wk.x0n;
   for (int i = 0; i < n; i++) x0n[i] = x[i];
   eval_f(x, f);
   int nfev = 1;
   eval_jac(x, f);
   double cost = 0.5 * dot(f, f, mres);
-  double v[NMAX], dv[NMAX], d[NMAX], diag_h[NMAX], g_h[NMAX], Bh[NMAX][NMAX], Aw[NMAX][NMAX], V[NMAX][NMAX], w[NMAX], s[NMAX], suf[NMAX];
+  double (&v)[NMAX] = wk.v, (&dv)[NMAX] = wk.dv, (&d)[NMAX] = wk.d, (&diag_h)[NMAX] = wk.diag_h, (&g_h)[NMAX] = wk.g_h;
+  double (&Bh)[NMAX][NMAX] = wk.Bh, (&Aw)[NMAX][NMAX] = wk.Aw, (&V)[NMAX][NMAX] = wk.V;
+  double (&w)[NMAX] = wk.w, (&s)[NMAX] = wk.s, (&suf)[NMAX] = wk.suf, (&t0)[NMAX] = wk.t0;
   cl_scaling(x, g, lb, ub, n, v, dv);
-  double t0[NMAX];
   for (int i = 0; i < n; i++) t0[i] = x0n[i] / N::sqrt(v[i]);
   double Delta = norm(t0, n);
   if (Delta == 0.0) Delta = 1.0;
@@ -265,7 +278,7 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
     // Gauss-Newton step p = -A^{-1} g_h by Cholesky.  When A is safely positive definite and the step lies inside the
     // trust region this is what solve_lsq_trust_region returns (full-rank branch, alpha = 0) and the eigen-decomposition
     // is never needed; otherwise (trust region active, or A close to singular) the decomposition is computed lazily.
-    double p_gn[NMAX], Lc[NMAX][NMAX];
+    double (&p_gn)[NMAX] = wk.p_gn, (&Lc)[NMAX][NMAX] = wk.Lc;
     bool gn_ok = true, have_eig = false;
     {
       double dmax = 0;
@@ -288,9 +301,9 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
     }
     const double theta = tmax(0.995, 1.0 - g_norm);
     double actual_reduction = -1.0, cost_new = cost;
-    double x_new[NMAX], f_new[6 + 2 * NMAX];
+    double (&x_new)[NMAX] = wk.x_new, (&f_new)[6 + 2 * NMAX] = wk.f_new;
     while (actual_reduction <= 0.0 && nfev < max_nfev) {
-      double p_h[NMAX], p[NMAX], step[NMAX], step_h[NMAX], predicted;
+      double (&p_h)[NMAX] = wk.p_h, (&p)[NMAX] = wk.p, (&step)[NMAX] = wk.step, (&step_h)[NMAX] = wk.step_h, predicted;
       if (gn_ok && norm(p_gn, n) <= Delta) {
         for (int i = 0; i < n; i++) p_h[i] = p_gn[i];
         alpha = 0.0;
@@ -305,12 +318,12 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
             suf[i] = r;
           }
         }
-        solve_lsq_trust_region(n, mres, suf, s, V, Delta, &alpha, p_h);
+        solve_lsq_trust_region(n, mres, suf, s, V, Delta, &alpha, p_h, wk.t);
       }
       for (int i = 0; i < n; i++) p[i] = d[i] * p_h[i];
       // ---- trf.py: select_step
       {
-        double xp[NMAX];
+        double (&xp)[NMAX] = wk.xp;
         for (int i = 0; i < n; i++) xp[i] = x[i] + p[i];
         auto evalq = [&](const double* sv) {   // evaluate_quadratic(J_h, g_h, s, diag_h)
           double q = quad(Bh, sv, sv, n);
@@ -321,9 +334,9 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
           for (int i = 0; i < n; i++) { step[i] = p[i]; step_h[i] = p_h[i]; }
           predicted = -evalq(p_h);
         } else {
-          int hits[NMAX];
-          const double p_stride = step_size_to_bound(x, p, lb, ub, n, hits);
-          double r_h[NMAX], r[NMAX], x_on_bound[NMAX];
+          int (&hits)[NMAX] = wk.hits;
+          const double p_stride = step_size_to_bound(x, p, lb, ub, n, hits, wk.steps);
+          double (&r_h)[NMAX] = wk.r_h, (&r)[NMAX] = wk.r, (&x_on_bound)[NMAX] = wk.x_on_bound;
           for (int i = 0; i < n; i++) { r_h[i] = hits[i] != 0 ? -p_h[i] : p_h[i]; r[i] = d[i] * r_h[i]; }
           for (int i = 0; i < n; i++) { p[i] *= p_stride; p_h[i] *= p_stride; x_on_bound[i] = x[i] + p[i]; }
           // intersect_trust_region(p_h, r_h, Delta): positive root
@@ -335,7 +348,7 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
             const double t1 = q / qa, t2 = qc / q;
             to_tr = t1 < t2 ? t2 : t1;
           }
-          const double to_bound = step_size_to_bound(x_on_bound, r, lb, ub, n, nullptr);
+          const double to_bound = step_size_to_bound(x_on_bound, r, lb, ub, n, nullptr, wk.steps);
           double r_stride = tmin(to_bound, to_tr), r_stride_l, r_stride_u;
           if (r_stride > 0) {
             r_stride_l = (1.0 - theta) * p_stride / r_stride;
@@ -353,10 +366,10 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
           }
           for (int i = 0; i < n; i++) { p[i] *= theta; p_h[i] *= theta; }
           const double p_value = evalq(p_h);
-          double ag_h[NMAX], ag[NMAX];
+          double (&ag_h)[NMAX] = wk.ag_h, (&ag)[NMAX] = wk.ag;
           for (int i = 0; i < n; i++) { ag_h[i] = -g_h[i]; ag[i] = d[i] * ag_h[i]; }
           const double to_tr2 = Delta / norm(ag_h, n);
-          const double to_bound2 = step_size_to_bound(x, ag, lb, ub, n, nullptr);
+          const double to_bound2 = step_size_to_bound(x, ag, lb, ub, n, nullptr, wk.steps);
           double ag_stride = to_bound2 < to_tr2 ? theta * to_bound2 : to_tr2, ag_value;
           double qa = quad(Bh, ag_h, ag_h, n), qb = dot(g_h, ag_h, n);
           for (int i = 0; i < n; i++) qa += ag_h[i] * diag_h[i] * ag_h[i];

@@ -41,6 +41,12 @@ struct KmArgs {
   int n, autoreset;
   unsigned long long seed, env0;
   int G, epb, grid;
+  // Cost-ordered walk (km_api.cu: order_envs): order[i] = env processed at position i (descending cost of the previous
+  // step, so that the envs sharing a CTA / warp need similar numbers of Newton iterations); tile_counter = dynamic tile
+  // fetch (CTAs take the next tile when they finish one: longest tiles first, balanced finish).  Both may be null.
+  const int* order;
+  int* tile_counter;
+  int trf_bytes;   // extra dynamic shared memory per env: work arrays of the exact-parity IK (ik_mode = 1), else 0
   int lpw;   // thread-per-env (local) mapping: active lanes per warp (envs of a CTA are spread over its warps)
   int tpl_small_regs;   // thread-per-env (local): use the 128-register instantiation even for CTAs of <= 256 threads (several CTAs per SM)
   cudaStream_t stream;
@@ -54,7 +60,7 @@ struct KmVtable {
   cudaError_t (*reset)(const KmArgs&);
   cudaError_t (*contacts)(const KmArgs&);
   // opt in to the dynamic shared memory of (G, epb); returns resident CTAs per SM through *ctas_per_sm
-  cudaError_t (*prepare)(int G, int epb, int* ctas_per_sm);
+  cudaError_t (*prepare)(int G, int epb, int extra_per_env, int* ctas_per_sm);
   // camera observations: one record of floats per env (camera frame + primitive list) from the stored state
   int render_rec_floats;
   double (*table_z)(const void* host_model);
@@ -129,28 +135,37 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
   StepOut<T> o = {(T*)a.obs, (T*)a.final_obs, (T*)a.reward, a.trunc, a.term, a.con_flags, a.ncon, a.con_geoms, Dim<S>::MAXCON, a.clk,
                   (T*)a.ep_return, (T*)a.episode_return, (T*)a.final_return, (T*)a.sim_time, a.is_success, a.step_out, a.episode_out,
                   a.totals ? cta_totals : nullptr};
-  // every warp walks the same number of tiles so that the groups sharing a warp can reconverge
-  for (long tile = (long)blockIdx.x * a.epb; tile < a.n; tile += (long)gridDim.x * a.epb) {
-    const long env = tile + slot;
-    const bool valid = env < a.n;
+  // every warp walks the same tiles so that the groups sharing a warp can reconverge
+  __shared__ long next_tile;
+  const long ntiles = ((long)a.n + a.epb - 1) / a.epb;
+  for (long t = blockIdx.x; t < ntiles;) {
+    const long tile = t * a.epb, idx = tile + slot;
+    const bool valid = idx < a.n;
     if (G < 32) {
       __syncwarp();
       g.wmask = __all_sync(0xffffffffu, valid) ? 0xffffffffu : g.mask;
     }
     // env slots past the end of the batch shadow the tile's first env (the CTA marches in phase) and store nothing
-    const long envc = valid ? env : tile;
+    const long idxc = valid ? idx : tile;
+    const long envc = a.order ? (long)a.order[idxc] : idxc;
     const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr,
                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     load_state<S, T, G>(e, a, envc, g);
     env_step<S, T, G>(e, m, g, a.act + envc * m.act_dim, valid ? o : none, envc, a.autoreset, a.seed, a.env0);
     if (valid) {
-      store_state<S, T, G>(e, a, env, g);
+      store_state<S, T, G>(e, a, envc, g);
       if (g.lane == 0) {
-        if (a.niter) a.niter[env] = e.solver_niter;
-        if (a.ls) a.ls[env] = e.ls_evals;
+        if (a.niter) a.niter[envc] = e.solver_niter;
+        if (a.ls) a.ls[envc] = e.ls_evals;
       }
     }
     g.sync();
+    if (a.tile_counter) {
+      __syncthreads();
+      if (threadIdx.x == 0) next_tile = (long)gridDim.x + atomicAdd(a.tile_counter, 1);
+      __syncthreads();
+      t = next_tile;
+    } else t += gridDim.x;
   }
   flush_totals(a, cta_totals);
 }
@@ -196,20 +211,28 @@ template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __lau
     const StepOut<T> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, Dim<S>::MAXCON, nullptr,
                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const long tiles = ((long)a.n + a.epb - 1) / a.epb;
-    for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    __shared__ long next_tile;
+    for (long tile = blockIdx.x; tile < tiles;) {
       // envs of the tile are dealt to the warps lpw at a time: with few envs per SM every scheduler still gets a
       // warp, and a warp only waits for the slowest of its own lpw envs
       const int lane = threadIdx.x & 31, slot = (threadIdx.x >> 5) * a.lpw + lane;
-      const long env = tile * a.epb + slot;
-      const bool valid = lane < a.lpw && slot < a.epb && env < a.n;
-      const long envc = valid ? env : tile * a.epb;
+      const long idx = tile * a.epb + slot;
+      const bool valid = lane < a.lpw && slot < a.epb && idx < a.n;
+      const long idxc = valid ? idx : tile * a.epb;
+      const long envc = a.order ? (long)a.order[idxc] : idxc;
       load_state<S, T, 1>(e, a, envc, g);
       env_step<S, T, 1>(e, m, g, a.act + envc * m.act_dim, valid ? o : none, envc, a.autoreset, a.seed, a.env0);
       if (valid) {
-        store_state<S, T, 1>(e, a, env, g);
-        if (a.niter) a.niter[env] = e.solver_niter;
-        if (a.ls) a.ls[env] = e.ls_evals;
+        store_state<S, T, 1>(e, a, envc, g);
+        if (a.niter) a.niter[envc] = e.solver_niter;
+        if (a.ls) a.ls[envc] = e.ls_evals;
       }
+      if (a.tile_counter) {
+        __syncthreads();
+        if (threadIdx.x == 0) next_tile = (long)gridDim.x + atomicAdd(a.tile_counter, 1);
+        __syncthreads();
+        tile = next_tile;
+      } else tile += gridDim.x;
     }
     flush_totals(a, cta_totals);
     return;
@@ -302,7 +325,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
 template <class S, typename T> struct Launch {
   typedef Dim<S> D;
   template <int G> static cudaError_t run(int which, const KmArgs& a) {
-    const size_t sm = smem_bytes<S, T>(a.epb);
+    const size_t sm = smem_bytes<S, T>(a.epb) + (size_t)a.epb * a.trf_bytes;
     const dim3 block(a.epb * G), grid(a.grid);
     if (which == 0) k_env_step<S, T, G><<<grid, block, sm, a.stream>>>(a);
     else if (which == 1) k_reset<S, T, G><<<grid, block, sm, a.stream>>>(a);
@@ -342,7 +365,7 @@ template <class S, typename T> struct Launch {
     k_render_setup<S, T, 32><<<dim3(grid), dim3(128), smem_bytes<S, T>(4), a.stream>>>(b, P, recs);
     return cudaGetLastError();
   }
-  template <int G> static cudaError_t prep(int epb, int* ctas) {
+  template <int G> static cudaError_t prep(int epb, int extra, int* ctas) {
     // the attribute is per function, not per handle: always opt in to the device maximum so that handles with
     // different envs-per-CTA can coexist in one process
     int dev = 0, optin = 0;
@@ -352,11 +375,11 @@ template <class S, typename T> struct Launch {
     if ((err = cudaFuncSetAttribute(k_env_step<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)KM_SMEM_STATIC)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(k_reset<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)KM_SMEM_STATIC)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(k_contacts<S, T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)KM_SMEM_STATIC)) != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, smem_bytes<S, T>(epb));
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step<S, T, G>, epb * G, smem_bytes<S, T>(epb) + (size_t)epb * extra);
   }
-  static cudaError_t prepare(int G, int epb, int* ctas) {
+  static cudaError_t prepare(int G, int epb, int extra, int* ctas) {
     if (G == 1) {
-      cudaError_t err = prep<32>(4, ctas);
+      cudaError_t err = prep<32>(4, 0, ctas);
       if (err != cudaSuccess) return err;
       int dev = 0, optin = 0;
       if ((err = cudaGetDevice(&dev)) != cudaSuccess) return err;
@@ -365,7 +388,7 @@ template <class S, typename T> struct Launch {
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, false>, (epb + 31) / 32 * 32, Tpe<S, T>::smem(epb));
     }
     if (G == 2) {
-      cudaError_t err = prep<32>(4, ctas);
+      cudaError_t err = prep<32>(4, 0, ctas);
       if (err != cudaSuccess) return err;
       // the env records live in local memory: give the unified L1 / shared-memory array to the cache
       if ((err = cudaFuncSetAttribute(k_env_step_tpe<S, T, true, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1)) != cudaSuccess) return err;
@@ -373,8 +396,8 @@ template <class S, typename T> struct Launch {
       if (epb <= 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true, 256>, (epb + 31) / 32 * 32, model_smem<S, T>());
       return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, k_env_step_tpe<S, T, true, 512>, (epb + 31) / 32 * 32, model_smem<S, T>());
     }
-    if (G == 32) return prep<32>(epb, ctas);
-    if constexpr (D::NV <= 16) { if (G == 16) return prep<16>(epb, ctas); }
+    if (G == 32) return prep<32>(epb, extra, ctas);
+    if constexpr (D::NV <= 16) { if (G == 16) return prep<16>(epb, extra, ctas); }
     return cudaErrorInvalidValue;
   }
   static int fill(const km_model* fm, const km_task* tk, void* dst, std::string& err) {

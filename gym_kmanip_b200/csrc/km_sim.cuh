@@ -1309,7 +1309,21 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
   if constexpr (kTrf) trf = feasible && m.ik_mode == 1;
   if (trf) {
     // exact-parity mode: the reference's optimiser (scipy TRF) restated, km_ik_trf.cuh; one lane, fp64
-    if constexpr (kTrf) { if (g.lane == 0) ik_trf_serial<S, T>(e, b, m, a); }
+    if constexpr (kTrf) {
+      if (g.lane == 0) {
+#if defined(__CUDA_ARCH__)
+        // the solve's work arrays: this env's slice of the dynamic shared memory behind the env records (km_launch.cuh)
+        extern __shared__ __align__(16) unsigned char km_dyn_smem[];
+        constexpr size_t model_b = (sizeof(Model<S, T>) + 15) / 16 * 16, env_b = (sizeof(E) + 15) / 16 * 16;
+        const int epb = blockDim.x / G, slot = threadIdx.x / G;
+        trf::TrfWork& wk = *(trf::TrfWork*)(km_dyn_smem + model_b + (size_t)epb * env_b + (size_t)slot * sizeof(trf::TrfWork));
+#else
+        trf::TrfWork wk_local;
+        trf::TrfWork& wk = wk_local;
+#endif
+        ik_trf_serial<S, T>(e, b, m, a, wk);
+      }
+    }
     g.sync();
   } else if (feasible) {
     const double lam = 9e-3 * (6e-3 + 2e-6), reg = 9e-3;   // IK_JAC_REG * (IK_RES_REG_PREV + IK_RES_REG_HOME)

@@ -135,6 +135,13 @@ int km_dtype(km_handle h);
    envs_per_block: envs per CTA, 0 = choose.  km_create picks a default from the batch size.
    Handles created with km_task.ik_mode = 1 (exact-parity TRF IK) run in the lane-group mapping only: 1 / 2 are refused. */
 int km_configure(km_handle h, int lanes_per_env, int envs_per_block);
+/* Cost-ordered walk of the step kernel.  The envs of a CTA march through the sub-step in phase, so a tile of envs costs what
+   its slowest env costs, and an env's cost (Newton iterations: its contact state) persists from step to step.  When on,
+   km_step first buckets the envs by the line-search evaluations of their previous step (one small counting-sort launch,
+   most expensive first) and the CTAs fetch the tiles dynamically.  Results do not depend on it (every env is stepped
+   exactly as before; only the rollout totals' atomics change order).  mode: -1 = automatic (default: on when the
+   lane-group mapping walks more tiles than there are CTAs), 0 = off, 1 = on.  No counterpart in the reference. */
+int km_set_env_ordering(km_handle h, int mode);
 long long km_launch_count(km_handle h);   /* kernels launched by this handle so far */
 int km_launch_config(km_handle h, int* lanes_per_env, int* envs_per_block, int* grid, int* ctas_per_sm, int* smem_bytes);
 

@@ -268,3 +268,45 @@ def test_vector_env_episode_logging_from_device_ring_buffers(tmp_path):
             assert np.allclose(d["observations/qpos"][r], rows[4 + r][1], atol=1e-7) and np.all(d["action"][r] == np.float32(rows[4 + r][0]))
         assert not d["observations/qpos"][4:].any()
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id,lanes,epb", [("KManipSoloArmQPos", 32, 2), ("KManipSoloArm", 32, 3), ("KManipSoloArmQPos", 2, 64)])
+def test_cost_ordered_walk_changes_no_result(env_id, lanes, epb):
+    """km_set_env_ordering: the envs are walked in the order of their previous step's solver cost and the CTAs fetch tiles
+    dynamically; every env must come out bit-identical to the plain walk, the permutation must be a permutation (every env
+    stepped exactly once per step), and the automatic mode must switch it on only when there are more tiles than CTAs."""
+    import torch
+    from gym_kmanip_b200.batch_sim import BatchSim
+    n = 1500
+    sims = []
+    for mode in (0, 1):
+        sim = BatchSim(env_id, n, dtype="float32", seed=3)
+        sim.configure(lanes, epb)
+        sim.set_env_ordering(mode)
+        sim.reset()
+        sims.append(sim)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    for t in range(6):
+        act = torch.rand(n, sims[0].act_dim, device="cuda", generator=gen) * 2 - 1
+        outs = [[x.clone() for x in sim.step(act)] for sim in sims]
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        assert torch.equal(sims[0].step_count, sims[1].step_count) and bool((sims[1].step_count == t + 1).all())
+    assert torch.equal(sims[0].get_state()[0], sims[1].get_state()[0])
+    l0 = [s.launches for s in sims]
+    for s in sims:
+        s.step(act)
+    assert sims[0].launches - l0[0] == 1 and sims[1].launches - l0[1] == 2   # the counting sort is the second launch
+    tot = [s.episode_stats().cpu() for s in sims]
+    assert tot[0][1] == tot[1][1] == n * 7 and abs(float(tot[0][0] - tot[1][0])) < 1e-6 * abs(float(tot[0][0]))
+    # automatic mode: 1500 envs in tiles of `epb` are more tiles than CTAs only for the small lane-group tiles
+    auto = BatchSim(env_id, n, dtype="float32", seed=3)
+    cfg = auto.configure(lanes, epb)
+    auto.reset()
+    l1 = auto.launches
+    auto.step(act)
+    tiles = (n + cfg["envs_per_block"] - 1) // cfg["envs_per_block"]
+    assert auto.launches - l1 == (2 if (lanes >= 16 and tiles > cfg["grid"]) else 1)
+    for s in sims + [auto]:
+        s.close()
