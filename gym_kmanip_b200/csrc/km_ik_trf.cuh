@@ -130,10 +130,16 @@ KM_HD void minimize_quadratic_1d(double a, double b, double lo, double hi, doubl
 // symmetric eigen-decomposition by cyclic Jacobi: A (destroyed) -> eigenvalues w (descending), eigenvectors in columns of V
 KM_HD void eig_sym(double (*A)[NMAX], int n, double* w, double (*V)[NMAX]) {
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) V[i][j] = i == j ? 1.0 : 0.0;
+  // Convergence: the off-diagonal mass falls quadratically until it reaches the rounding floor of the rotations
+  // (off ~ 1e-32 diag); stop at 1e-30, or once a sweep no longer reduces an already negligible remainder.  (A threshold
+  // below the floor never triggers and every decomposition runs all 30 sweeps: the slowest envs of a batch spent 90 % of
+  // their step there.)
+  double prev_off = INF;
   for (int sweep = 0; sweep < 30; sweep++) {
     double off = 0, diag = 0;
     for (int i = 0; i < n; i++) { diag += A[i][i] * A[i][i]; for (int j = 0; j < i; j++) off += A[i][j] * A[i][j]; }
-    if (off <= 1e-34 * diag || off == 0.0) break;
+    if (off <= 1e-30 * diag || off == 0.0 || (off <= 1e-24 * diag && off > 0.25 * prev_off)) break;
+    prev_off = off;
     for (int p = 0; p < n - 1; p++)
       for (int q = p + 1; q < n; q++) {
         const double apq = A[p][q];

@@ -9,7 +9,8 @@ env = sys.argv[1] if len(sys.argv) > 1 else "KManipSoloArmQPos"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 epb = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-sim = BatchSim(env, n, dtype="float32", seed=0)
+ik_mode = int(os.environ.get("IK_MODE", "0"))
+sim = BatchSim(env, n, dtype="float32", seed=0, ik_mode=ik_mode)
 if lanes or epb:
     sim.configure(lanes, epb)
 print("launch", sim.launch_config())
@@ -37,6 +38,8 @@ for t in range(40):
         busy = c[:, :11].sum(1) + c[:, 12] + c[:, 13]          # everything but the barrier waits
         bq = torch.quantile(busy, torch.tensor([0.1, 0.5, 0.9, 0.99, 1.0], dtype=tp.dtype))
         print("   per-env busy cycles (no barrier waits) p10/p50/p90/p99/max: " + " ".join(f"{x:.0f}" for x in bq.tolist()))
+        bf = torch.quantile(c[:, 12], torch.tensor([0.1, 0.5, 0.9, 0.99, 1.0], dtype=tp.dtype))
+        print("   per-env before_step (action decode + IK) cycles p10/p50/p90/p99/max: " + " ".join(f"{x:.0f}" for x in bf.tolist()))
         top = torch.argsort(busy, descending=True)[:6]
         fl = sim.con_flags.cpu(); nc = sim.ncon.cpu()
         for i in top.tolist():
