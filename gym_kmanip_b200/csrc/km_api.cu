@@ -307,12 +307,12 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   const int per_sm = (n_envs + h->num_sms - 1) / h->num_sms;
   int rc;
   // envs per SM from which the thread-per-env kernel wins (measured crossovers with the register-resident warp-per-env
-  // solver, profiles/r02_notes.md: solo arm, joint actions: 6.3 vs 6.2e6 env-steps/s at 221 envs per SM, 6.7 vs 7.7e6 at 443;
-  // solo arm + IK: equal at 111; dual arm fp32: 1.65 vs 1.34e6 at 55, 1.9 vs 3.2e6 at 221; torso fp64: 1.65 vs 1.36e6 at 28,
-  // 1.55 vs 2.16e6 at 55; torso fp32: 3.4 vs 3.0e6 at 55)
+  // solver and the cost-ordered walk, profiles/r02_mapping_sweep.log: solo arm, joint actions: 6.75 vs 6.2e6 env-steps/s at
+  // 221 envs per SM, 7.0 vs 7.8e6 at 443; solo arm + IK: 3.9 vs 3.6e6 at 111; dual arm fp32: 2.05 vs 1.34e6 at 55, 2.2 vs
+  // 3.2e6 at 221; torso fp64: 1.69 vs 1.37e6 at 28, 1.65 vs 2.16e6 at 55; torso fp32: 3.6 vs 2.9e6 at 55, 3.7 vs 6.5e6 at 221)
   int tpe_from;
-  if (h->vt.nv <= 16) tpe_from = task->act_mode == 1 ? 300 : 110;
-  else tpe_from = dtype == KM_F64 ? 40 : 80;
+  if (h->vt.nv <= 16) tpe_from = task->act_mode == 1 ? 300 : 150;
+  else tpe_from = dtype == KM_F64 ? 40 : 100;
   if (per_sm >= tpe_from && h->ik_mode != 1) rc = configure(h, 2, 0);   // the exact-parity IK mode lives in the lane-group kernels
   else {
     h->G = 32;

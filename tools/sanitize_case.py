@@ -15,6 +15,19 @@ for env in ("KManipSoloArm", "KManipDualArm"):
         torch.cuda.synchronize()
         s.close()
         print(env, lanes, "ok", flush=True)
+# cost-ordered walk (counting sort + dynamic tile fetch) on small tiles, and the exact-parity IK (work arrays in dynamic
+# shared memory behind the env records)
+for env, lanes, epb, kw in (("KManipSoloArmQPos", 32, 1, {}), ("KManipSoloArm", 32, 2, dict(ik_mode=1)), ("KManipDualArm", 32, 3, dict(ik_mode=1))):
+    s = BatchSim(env, 333, dtype="float32", seed=1, max_episode_steps=3, **kw)
+    s.configure(lanes, epb)
+    s.set_env_ordering(1)
+    s.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(4):
+        s.step(torch.rand(333, s.act_dim, device="cuda", generator=gen) * 2 - 1, autoreset=True)
+    torch.cuda.synchronize()
+    s.close()
+    print(env, lanes, epb, kw, "ordered walk ok", flush=True)
 # camera observations: setup + pixel kernels, aligned (640 x 480) and unaligned (60 x 40) store paths, partial tiles
 for env, cams in (("KManipSoloArmVision", ("head", "grip_r")), ("KManipTorsoVision", ("top", "grip_l"))):
     s = BatchSim(env, 3, dtype="float32", seed=1)
