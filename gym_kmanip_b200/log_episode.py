@@ -7,8 +7,8 @@ of ``info``.  The reference's quirks are kept on purpose: the logged "qpos" / "q
 a_len columns (log_h5py.py:55; a_len is the number of action keys, env_base.py:191).
 
 h5py is not part of the build image: when it imports, ``episode_<k>.hdf5`` is written exactly as the reference does;
-otherwise the same arrays go to ``episode_<k>.npz`` under the same dataset names (``np.load(path)["observations/qpos"]``)
-with the attributes in a JSON string ``__attrs__``.  Camera datasets belong to the Vision ids, which are out of scope.
+otherwise the same tree is written as ``episode_<k>.hdf5`` by the minimal pure-Python writer ``hdf5_min.py``
+(fixed-length string / numeric attributes; bools as uint8).  Camera datasets of the Vision ids are not logged.
 """
 from __future__ import annotations
 
@@ -70,10 +70,33 @@ class EpisodeLog:
                 f.create_dataset("observations/qvel", data=self.qvel)
                 f.create_dataset("action", data=self.action)
         else:
-            self.path = self.stem + ".npz"
-            np.savez(self.path, **{"observations/qpos": self.qpos, "observations/qvel": self.qvel, "action": self.action,
-                                   "__attrs__": np.array(json.dumps({"sim": self.attrs["sim"], "metadata": self.metadata}))})
+            # no h5py in this image: the same tree through the minimal HDF5 writer of this package (version 0 superblock,
+            # symbol-table groups, contiguous datasets -- hdf5_min.py), so consumers of the ACT / LeRobot layout get .hdf5
+            from . import hdf5_min
+            self.path = self.stem + ".hdf5"
+            meta = {}
+            for key, value in self.metadata.items():
+                try:
+                    hdf5_min._attr_value(value)
+                    meta[key] = value
+                except (TypeError, ValueError):
+                    pass               # "Could not save ..." in the reference (log_h5py.py:21-24)
+            hdf5_min.write(self.path, {"action": self.action, "metadata": {},
+                                       "observations": {"images": {}, "qpos": self.qpos, "qvel": self.qvel}},
+                           attrs={"": {"sim": self.attrs["sim"]}, "metadata": meta})
         return self.path
+
+
+def read_episode(path: str):
+    """Reads an episode file written by this module: (qpos, qvel, action, root attrs, metadata attrs).  Uses h5py when it
+    imports, else the reader of hdf5_min (which parses exactly the subset of HDF5 that hdf5_min writes)."""
+    if HAVE_H5PY:                                          # pragma: no cover
+        with h5py.File(path, "r") as f:
+            return (f["observations/qpos"][:], f["observations/qvel"][:], f["action"][:], dict(f.attrs), dict(f["metadata"].attrs))
+    from . import hdf5_min
+    tree, attrs = hdf5_min.read(path)
+    assert tree["observations"]["images"] == {}
+    return tree["observations"]["qpos"], tree["observations"]["qvel"], tree["action"], attrs.get("", {}), attrs.get("metadata", {})
 
 
 def new(log_dir: str, info: Dict[str, Any]) -> EpisodeLog:

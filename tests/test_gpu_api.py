@@ -239,10 +239,11 @@ def test_single_env_episode_logging(tmp_path, monkeypatch):
     env.close()
     files = sorted(os.listdir(u.log_dir))
     assert [f.split(".")[0] for f in files] == ["episode_1", "episode_2"]
-    if files[0].endswith(".npz"):
-        d = np.load(os.path.join(u.log_dir, files[0]))
-        assert d["observations/qpos"].shape == (64, 10) and d["action"].shape == (64, 3)
-        assert d["observations/qpos"][:5].any() and not d["observations/qpos"][5:].any()
+    from gym_kmanip_b200.log_episode import read_episode
+    assert files[0].endswith(".hdf5")
+    qpos, qvel, action, attrs, meta = read_episode(os.path.join(u.log_dir, files[0]))
+    assert qpos.shape == (64, 10) and action.shape == (64, 3) and attrs["sim"]
+    assert qpos[:5].any() and not qpos[5:].any()
 
 
 @pytest.mark.gpu
@@ -261,12 +262,13 @@ def test_vector_env_episode_logging_from_device_ring_buffers(tmp_path):
         rows.append((act[63, env.action_layout["grip_r"].start].item(), src[63, :10].float().cpu().numpy()))
     files = sorted(os.listdir(tmp_path))
     assert [f.split(".")[0] for f in files] == ["env000000_episode_1", "env000000_episode_2", "env000063_episode_1", "env000063_episode_2"]
-    if files[-1].endswith(".npz"):
-        d = np.load(os.path.join(tmp_path, files[-1]))
-        assert d["observations/qpos"].shape == (64, 10) and d["action"].shape == (64, 2)
-        for r in range(4):
-            assert np.allclose(d["observations/qpos"][r], rows[4 + r][1], atol=1e-7) and np.all(d["action"][r] == np.float32(rows[4 + r][0]))
-        assert not d["observations/qpos"][4:].any()
+    from gym_kmanip_b200.log_episode import read_episode
+    assert files[-1].endswith(".hdf5")
+    qpos, qvel, action, attrs, meta = read_episode(os.path.join(tmp_path, files[-1]))
+    assert qpos.shape == (64, 10) and action.shape == (64, 2)
+    for r in range(4):
+        assert np.allclose(qpos[r], rows[4 + r][1], atol=1e-7) and np.all(action[r] == np.float32(rows[4 + r][0]))
+    assert not qpos[4:].any()
     env.close()
 
 

@@ -105,16 +105,9 @@ def test_episode_log_layout_follows_the_reference(tmp_path):
         rows.append((act, obs))
     path = log_episode.end(f)
     assert os.path.basename(path).startswith("episode_3.")
-    if path.endswith(".npz"):
-        d = np.load(path)
-        qpos, qvel, action = d["observations/qpos"], d["observations/qvel"], d["action"]
-        attrs = json.loads(str(d["__attrs__"]))
-        assert attrs["sim"] is True and attrs["metadata"]["q_len"] == 10 and attrs["metadata"]["episode"] == 3
-    else:                                  # pragma: no cover - h5py present
-        import h5py
-        with h5py.File(path) as d:
-            qpos, qvel, action = d["observations/qpos"][:], d["observations/qvel"][:], d["action"][:]
-            assert d.attrs["sim"] and d["metadata"].attrs["q_len"] == 10
+    assert path.endswith(".hdf5")
+    qpos, qvel, action, attrs, meta = log_episode.read_episode(path)
+    assert attrs["sim"] and meta["q_len"] == 10 and meta["episode"] == 3
     assert qpos.shape == (64, 10) and qvel.shape == (64, 10) and action.shape == (64, 3)
     for t, (act, obs) in enumerate(rows):
         assert np.allclose(qpos[t], obs["q_pos"], atol=1e-7) and np.allclose(qvel[t], obs["q_vel"], atol=1e-7)
@@ -144,16 +137,15 @@ def test_batch_episode_log_ring_buffers(tmp_path):
     names = sorted(os.path.basename(p).split(".")[0] for p in log.paths)
     assert names == ["env000101_episode_1", "env000101_episode_2", "env000104_episode_1", "env000104_episode_2"]
     path = [p for p in log.paths if "env000104_episode_2" in p][0]
-    if path.endswith(".npz"):
-        d = np.load(path)
-        qpos, qvel, action = d["observations/qpos"], d["observations/qvel"], d["action"]
-        meta = json.loads(str(d["__attrs__"]))["metadata"]
-        assert meta["env"] == 104 and meta["episode"] == 2 and meta["step"] == T and meta["env_id"] == "KManipSoloArm"
-        assert qpos.shape == (64, q_len) and action.shape == (64, 3)
-        for r in range(T):
-            act, obs, fin, done = hist[T + r]
-            src = fin if done[4] else obs
-            assert np.allclose(qpos[r], src[4, :q_len].numpy(), atol=1e-7) and np.allclose(qvel[r], src[4, q_len:2 * q_len].numpy(), atol=1e-7)
-            assert np.all(action[r] == act[4, 6].numpy())
-        assert not qpos[T:].any() and not action[T:].any()
+    from gym_kmanip_b200.log_episode import read_episode
+    assert path.endswith(".hdf5")
+    qpos, qvel, action, attrs, meta = read_episode(path)
+    assert meta["env"] == 104 and meta["episode"] == 2 and meta["step"] == T and meta["env_id"] == "KManipSoloArm" and attrs["sim"]
+    assert qpos.shape == (64, q_len) and action.shape == (64, 3) and qpos.dtype == np.float32
+    for r in range(T):
+        act, obs, fin, done = hist[T + r]
+        src = fin if done[4] else obs
+        assert np.allclose(qpos[r], src[4, :q_len].numpy(), atol=1e-7) and np.allclose(qvel[r], src[4, q_len:2 * q_len].numpy(), atol=1e-7)
+        assert np.all(action[r] == act[4, 6].numpy())
+    assert not qpos[T:].any() and not action[T:].any()
     assert int(log.row[0]) == 1 and log.qpos[1:].abs().sum() == 0   # the ninth step opened episode 3
