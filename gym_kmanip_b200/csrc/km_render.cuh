@@ -224,6 +224,32 @@ __device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, c
   for (int c = 0; c < 3; c++) rgb[c] = fminf(P.mat[mat][c] * dif[c] + P.mat_specular * spc[c], 1.0f);
 }
 
+// The same for a point of the table plane (most pixels of every camera): the normal is +z, so every N.L is a constant of
+// the launch (`tdif` = ambient + sum of the lights' diffuse terms, formed once per thread) and the half vector needs no
+// normalisation of its own: |L + V|^2 = 2 + 2 L.V for unit L and V, hence N.H = (L_z + V_z) rsqrt(2 + 2 L.V).  About a
+// third of the instructions of shade(); rounding differs from it by an ulp here and there (one grey level at most).
+__device__ __forceinline__ void shade_table(const KmRenderParams& P, const float* d, const float* tdif, float* rgb) {
+  const float vz = -d[2], nv = fmaxf(vz, 0.0f);
+  float dif[3] = {tdif[0], tdif[1], tdif[2]}, spc[3] = {0, 0, 0};
+  for (int c = 0; c < 3; c++) dif[c] += P.head_diffuse[c] * nv;
+  if (nv > P.spec_cut) {
+    const float s = shin_pow(nv, P.shin_squarings);
+    for (int c = 0; c < 3; c++) spc[c] += P.head_specular[c] * s;
+  }
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    if (l < P.nlight && P.ldir[l][2] > 0.0f) {
+      const float lv = -rdot(P.ldir[l], d);
+      const float nh = (P.ldir[l][2] + vz) * rsqrtf(fmaxf(2.0f + 2.0f * lv, 1e-12f));
+      if (nh > P.spec_cut) {
+        const float sh = shin_pow(nh, P.shin_squarings);
+        for (int c = 0; c < 3; c++) spc[c] += P.lspecular[l][c] * sh;
+      }
+    }
+  }
+  for (int c = 0; c < 3; c++) rgb[c] = fminf(P.mat[KM_MAT_TABLE][c] * dif[c] + P.mat_specular * spc[c], 1.0f);
+}
+
 __global__ void __launch_bounds__(256) k_render_pixels(const float* __restrict__ recs, unsigned char* __restrict__ out, KmRenderParams P) {
   __shared__ float rec[KM_REC_HDR + KM_PRIM_FLOATS * KM_RENDER_MAXPRIM];
   __shared__ unsigned s_mask;
@@ -276,8 +302,13 @@ __global__ void __launch_bounds__(256) k_render_pixels(const float* __restrict__
   __syncthreads();
   const unsigned mask = s_mask;
   const float o[3] = {rec[0], rec[1], rec[2]};
+  float tdif[3] = {P.ambient[0], P.ambient[1], P.ambient[2]};   // diffuse light on the table plane (normal +z), headlight aside
+#pragma unroll
+  for (int l = 0; l < 4; l++)
+    if (l < P.nlight && P.ldir[l][2] > 0.0f)
+      for (int c = 0; c < 3; c++) tdif[c] += P.ldiffuse[l][c] * P.ldir[l][2];
 #ifndef KM_RENDER_UNROLL
-#define KM_RENDER_UNROLL 4
+#define KM_RENDER_UNROLL 1   // measured: 11.5 ms per 4096 x 640 x 480 launch against 12.0 (2) and 12.6 (4) -- the unrolled body (100 KB of SASS at 4) misses the instruction cache
 #endif
   constexpr int kUnroll = KM_RENDER_UNROLL;
 #pragma unroll kUnroll
@@ -295,7 +326,8 @@ __global__ void __launch_bounds__(256) k_render_pixels(const float* __restrict__
         const int pi = __ffs(mm) - 1;
         hit_prim(rec + KM_REC_HDR + KM_PRIM_FLOATS * pi, o, d, tbest, nrm, mat);
       }
-      if (mat >= 0) {
+      if (mat == KM_MAT_TABLE) shade_table(P, d, tdif, rgb);
+      else if (mat >= 0) {
         const float V[3] = {-d[0], -d[1], -d[2]};
         shade(P, nrm, V, mat, rgb);
       }
