@@ -520,11 +520,12 @@ int km_render(km_handle h, const km_camera* cam, const km_visual* vis, unsigned 
   P.cam_link = cam->link; P.tgt_link = cam->target_link;
   KmArgs a = base_args(h, stream);
   KM_CUDA(h->vt.render_setup(a, P, h->d_recs));
-  const long long nblocks = (long long)P.tiles_x * P.tiles_y * h->n;
-  if (nblocks > 2147483647LL) return fail(KM_ERR_ARG, "km_render: image batch too large for one launch");
-  const dim3 grid((unsigned)nblocks);
-  km::k_render_pixels<<<grid, 256, 0, (cudaStream_t)stream>>>(h->d_recs, rgb_dev, P);
-  KM_CUDA(cudaGetLastError());
+  // grid = (tile column, tile row, env): at most 65535 envs per launch, larger batches in chunks
+  for (int e0 = 0; e0 < h->n; e0 += 65535) {
+    const int ne = h->n - e0 < 65535 ? h->n - e0 : 65535;
+    km::k_render_pixels<<<dim3(P.tiles_x, P.tiles_y, ne), km::KM_RENDER_THREADS, 0, (cudaStream_t)stream>>>(h->d_recs, rgb_dev, P, e0);
+    KM_CUDA(cudaGetLastError());
+  }
   h->launches += 2;
   return KM_OK;
 }

@@ -14,8 +14,9 @@
 //   k_render_setup<S,T,G>  per env (lane group): state -> forward kinematics -> one record of floats
 //                          [camera origin + axes | primitive list]  (KM_REC_HDR + 16 floats per primitive)
 //   k_render_pixels        scene-independent, one CTA per 32 x 32 pixel tile per env: record -> shared memory, warp 0
-//                          culls the primitives against the tile's cone, 256 threads shade 4 pixels each into a
-//                          shared-memory tile, the tile goes out as 16-byte streaming stores (rows of 96 bytes).
+//                          culls the primitives against the tile's cone, 128 threads shade one pixel column of eight rows
+//                          each into a shared-memory tile (tiles that see no primitive: table plane / background loop
+//                          only), the tile goes out as 16-byte streaming stores (rows of 96 bytes).
 // The pixel kernel's algorithmic HBM traffic is the image itself (W*H*3 bytes per env) plus one ~1 KB record.
 #pragma once
 #include "km_model.cuh"
@@ -225,10 +226,11 @@ __device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, c
 }
 
 // The same for a point of the table plane (most pixels of every camera): the normal is +z, so every N.L is a constant of
-// the launch (`tdif` = ambient + sum of the lights' diffuse terms, formed once per thread) and the half vector needs no
-// normalisation of its own: |L + V|^2 = 2 + 2 L.V for unit L and V, hence N.H = (L_z + V_z) rsqrt(2 + 2 L.V).  About a
-// third of the instructions of shade(); rounding differs from it by an ulp here and there (one grey level at most).
-__device__ __forceinline__ void shade_table(const KmRenderParams& P, const float* d, const float* tdif, float* rgb) {
+// the launch (`tdif` = ambient + sum of the lights' diffuse terms, formed once per thread; `lmask` = the lights above the
+// plane) and the half vector needs no normalisation of its own: |L + V|^2 = 2 + 2 L.V for unit L and V, hence
+// N.H = (L_z + V_z) rsqrt(2 + 2 L.V).  About a third of the instructions of shade(); rounding differs from it by an ulp
+// here and there (one grey level at most).
+__device__ __forceinline__ void shade_table(const KmRenderParams& P, const float* d, const float* tdif, unsigned lmask, float* rgb) {
   const float vz = -d[2], nv = fmaxf(vz, 0.0f);
   float dif[3] = {tdif[0], tdif[1], tdif[2]}, spc[3] = {0, 0, 0};
   for (int c = 0; c < 3; c++) dif[c] += P.head_diffuse[c] * nv;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void shade_table(const KmRenderParams& P, const float
   }
 #pragma unroll
   for (int l = 0; l < 4; l++) {
-    if (l < P.nlight && P.ldir[l][2] > 0.0f) {
+    if ((lmask >> l) & 1u) {
       const float lv = -rdot(P.ldir[l], d);
       const float nh = (P.ldir[l][2] + vz) * rsqrtf(fmaxf(2.0f + 2.0f * lv, 1e-12f));
       if (nh > P.spec_cut) {
@@ -250,16 +252,19 @@ __device__ __forceinline__ void shade_table(const KmRenderParams& P, const float
   for (int c = 0; c < 3; c++) rgb[c] = fminf(P.mat[KM_MAT_TABLE][c] * dif[c] + P.mat_specular * spc[c], 1.0f);
 }
 
-__global__ void __launch_bounds__(256) k_render_pixels(const float* __restrict__ recs, unsigned char* __restrict__ out, KmRenderParams P) {
+// One CTA of 128 threads per 32 x 32 pixel tile (blockIdx.x, blockIdx.y) of env env0 + blockIdx.z; every thread owns one
+// pixel column of the tile and walks eight rows, so the horizontal part of the ray and everything that depends on the
+// launch or the env only (camera axes, light terms of the table plane) is formed once per thread.  Tiles that see no
+// primitive (most of them) take a loop that knows only the table plane and the background.
+constexpr int KM_RENDER_THREADS = 128, KM_RENDER_ROWS = KM_RENDER_TILE * KM_RENDER_TILE / KM_RENDER_THREADS;
+__global__ void __launch_bounds__(KM_RENDER_THREADS) k_render_pixels(const float* __restrict__ recs, unsigned char* __restrict__ out, KmRenderParams P, int env0) {
   __shared__ float rec[KM_REC_HDR + KM_PRIM_FLOATS * KM_RENDER_MAXPRIM];
   __shared__ unsigned s_mask;
   __shared__ __align__(16) unsigned char tile[KM_RENDER_TILE * KM_RENDER_TILE * 3];
-  // blockIdx.x = env * tiles + tile (grid.x reaches 2^31 - 1: no limit on the batch worth naming)
-  const int ntiles = P.tiles_x * P.tiles_y;
-  const int tid = threadIdx.x, env = blockIdx.x / ntiles, tl = blockIdx.x % ntiles;
-  const int tx0 = (tl % P.tiles_x) * KM_RENDER_TILE, ty0 = (tl / P.tiles_x) * KM_RENDER_TILE;
+  const int tid = threadIdx.x, env = env0 + blockIdx.z;
+  const int tx0 = blockIdx.x * KM_RENDER_TILE, ty0 = blockIdx.y * KM_RENDER_TILE;
   const float* src = recs + (size_t)env * P.rec_floats;
-  for (int i = tid; i < P.rec_floats; i += 256) rec[i] = src[i];
+  for (int i = tid; i < P.rec_floats; i += KM_RENDER_THREADS) rec[i] = src[i];
   __syncthreads();
   if (tid < 32) {
     // cull: keep the primitives whose bounding sphere meets the cone around the tile (axis = ray through the tile
@@ -302,52 +307,74 @@ __global__ void __launch_bounds__(256) k_render_pixels(const float* __restrict__
   __syncthreads();
   const unsigned mask = s_mask;
   const float o[3] = {rec[0], rec[1], rec[2]};
-  float tdif[3] = {P.ambient[0], P.ambient[1], P.ambient[2]};   // diffuse light on the table plane (normal +z), headlight aside
+  // per-thread constants: light terms of the table plane (normal +z), this pixel column's part of the ray
+  float tdif[3] = {P.ambient[0], P.ambient[1], P.ambient[2]};
+  unsigned lmask = 0;
 #pragma unroll
   for (int l = 0; l < 4; l++)
-    if (l < P.nlight && P.ldir[l][2] > 0.0f)
+    if (l < P.nlight && P.ldir[l][2] > 0.0f) {
+      lmask |= 1u << l;
       for (int c = 0; c < 3; c++) tdif[c] += P.ldiffuse[l][c] * P.ldir[l][2];
-#ifndef KM_RENDER_UNROLL
-#define KM_RENDER_UNROLL 1   // measured: 11.5 ms per 4096 x 640 x 480 launch against 12.0 (2) and 12.6 (4) -- the unrolled body (100 KB of SASS at 4) misses the instruction cache
-#endif
-  constexpr int kUnroll = KM_RENDER_UNROLL;
-#pragma unroll kUnroll
-  for (int k = 0; k < 4; k++) {
-    const int lx = tid & 31, ly = (tid >> 5) + 8 * k;
-    const int px = tx0 + lx, py = ty0 + ly;
-    float rgb[3] = {0, 0, 0};
-    if (px < P.W && py < P.H) {
-      float d[3], nrm[3] = {0, 0, 1};
-      pixel_ray(P, rec, (float)px + 0.5f, (float)py + 0.5f, d);
-      float tbest = 3.0e38f;
-      int mat = -1;
-      if (d[2] < 0.0f && o[2] > P.tab_z) { tbest = (P.tab_z - o[2]) / d[2]; mat = KM_MAT_TABLE; }
-      for (unsigned mm = mask; mm; mm &= mm - 1) {
-        const int pi = __ffs(mm) - 1;
-        hit_prim(rec + KM_REC_HDR + KM_PRIM_FLOATS * pi, o, d, tbest, nrm, mat);
-      }
-      if (mat == KM_MAT_TABLE) shade_table(P, d, tdif, rgb);
-      else if (mat >= 0) {
-        const float V[3] = {-d[0], -d[1], -d[2]};
-        shade(P, nrm, V, mat, rgb);
-      }
     }
-    unsigned char* t = tile + ly * (KM_RENDER_TILE * 3) + lx * 3;
-    for (int c = 0; c < 3; c++) t[c] = (unsigned char)(int)(rgb[c] * 255.0f + 0.5f);
+  const int lx = tid & 31, px = tx0 + lx, ly0 = tid >> 5;
+  const float inv = 1.0f / P.focal, dx = ((float)px + 0.5f - 0.5f * (float)P.W) * inv;
+  const float ay[3] = {rec[6], rec[7], rec[8]};
+  const float base[3] = {rec[3] * dx - rec[9], rec[4] * dx - rec[10], rec[5] * dx - rec[11]};
+  const bool above = o[2] > P.tab_z;
+  if (mask == 0u) {
+    // table plane and background only
+#pragma unroll 2
+    for (int k = 0; k < KM_RENDER_ROWS; k++) {
+      const int ly = ly0 + 4 * k, py = ty0 + ly;
+      float rgb[3] = {0, 0, 0};
+      if (px < P.W && py < P.H) {
+        const float dy = -((float)py + 0.5f - 0.5f * (float)P.H) * inv;
+        float d[3] = {base[0] + ay[0] * dy, base[1] + ay[1] * dy, base[2] + ay[2] * dy};
+        rnorm(d);
+        if (above && d[2] < 0.0f) shade_table(P, d, tdif, lmask, rgb);
+      }
+      unsigned char* t = tile + ly * (KM_RENDER_TILE * 3) + lx * 3;
+      for (int c = 0; c < 3; c++) t[c] = (unsigned char)(int)(rgb[c] * 255.0f + 0.5f);
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < KM_RENDER_ROWS; k++) {
+      const int ly = ly0 + 4 * k, py = ty0 + ly;
+      float rgb[3] = {0, 0, 0};
+      if (px < P.W && py < P.H) {
+        const float dy = -((float)py + 0.5f - 0.5f * (float)P.H) * inv;
+        float d[3] = {base[0] + ay[0] * dy, base[1] + ay[1] * dy, base[2] + ay[2] * dy}, nrm[3] = {0, 0, 1};
+        rnorm(d);
+        float tbest = 3.0e38f;
+        int mat = -1;
+        if (above && d[2] < 0.0f) { tbest = (P.tab_z - o[2]) / d[2]; mat = KM_MAT_TABLE; }
+        for (unsigned mm = mask; mm; mm &= mm - 1) {
+          const int pi = __ffs(mm) - 1;
+          hit_prim(rec + KM_REC_HDR + KM_PRIM_FLOATS * pi, o, d, tbest, nrm, mat);
+        }
+        if (mat == KM_MAT_TABLE) shade_table(P, d, tdif, lmask, rgb);
+        else if (mat >= 0) {
+          const float V[3] = {-d[0], -d[1], -d[2]};
+          shade(P, nrm, V, mat, rgb);
+        }
+      }
+      unsigned char* t = tile + ly * (KM_RENDER_TILE * 3) + lx * 3;
+      for (int c = 0; c < 3; c++) t[c] = (unsigned char)(int)(rgb[c] * 255.0f + 0.5f);
+    }
   }
   __syncthreads();
   unsigned char* img = out + (size_t)env * P.W * P.H * 3;
   const int rows = min(KM_RENDER_TILE, P.H - ty0);
   if ((P.W * 3) % 16 == 0 && tx0 + KM_RENDER_TILE <= P.W) {
     // full-width tile on a 16-byte-aligned pitch: each row is 96 contiguous bytes = six 16-byte streaming stores
-    for (int i = tid; i < rows * 6; i += 256) {
+    for (int i = tid; i < rows * 6; i += KM_RENDER_THREADS) {
       const int row = i / 6, seg = i % 6;
       const uint4 v = *(const uint4*)(tile + row * 96 + seg * 16);
       __stcs((uint4*)(img + ((size_t)(ty0 + row) * P.W + tx0) * 3 + seg * 16), v);
     }
   } else {
     const int cols = min(KM_RENDER_TILE, P.W - tx0) * 3;
-    for (int i = tid; i < rows * cols; i += 256) {
+    for (int i = tid; i < rows * cols; i += KM_RENDER_THREADS) {
       const int row = i / cols, cb = i % cols;
       img[((size_t)(ty0 + row) * P.W + tx0) * 3 + cb] = tile[row * 96 + cb];
     }
