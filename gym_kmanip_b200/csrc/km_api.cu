@@ -523,7 +523,8 @@ int km_render(km_handle h, const km_camera* cam, const km_visual* vis, unsigned 
   // grid = (tile column, tile row, env): at most 65535 envs per launch, larger batches in chunks
   for (int e0 = 0; e0 < h->n; e0 += 65535) {
     const int ne = h->n - e0 < 65535 ? h->n - e0 : 65535;
-    km::k_render_pixels<<<dim3(P.tiles_x, P.tiles_y, ne), km::KM_RENDER_THREADS, 0, (cudaStream_t)stream>>>(h->d_recs, rgb_dev, P, e0);
+    if (P.shin_squarings == 6) km::k_render_pixels<6><<<dim3(P.tiles_x, P.tiles_y, ne), km::KM_RENDER_THREADS, 0, (cudaStream_t)stream>>>(h->d_recs, rgb_dev, P, e0);
+    else km::k_render_pixels<-1><<<dim3(P.tiles_x, P.tiles_y, ne), km::KM_RENDER_THREADS, 0, (cudaStream_t)stream>>>(h->d_recs, rgb_dev, P, e0);
     KM_CUDA(cudaGetLastError());
   }
   h->launches += 2;

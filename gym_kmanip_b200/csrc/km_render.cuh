@@ -190,20 +190,27 @@ __device__ __forceinline__ void hit_prim(const float* p, const float* o, const f
   }
 }
 
-// x^(2^k) by repeated squaring; k = 6 (MuJoCo's default shininess 0.5 -> exponent 64) is unrolled
-__device__ __forceinline__ float shin_pow(float x, int k) {
-  if (k == 6) { x *= x; x *= x; x *= x; x *= x; x *= x; x *= x; return x; }
-  for (int i = 0; i < k; i++) x *= x;
-  return x;
+// x^(2^k) by repeated squaring.  KS >= 0: k is the compile-time constant KS (MuJoCo's default shininess 0.5 -> exponent 64,
+// k = 6: the instantiation every shipped scene uses); KS < 0: run-time k
+template <int KS> __device__ __forceinline__ float shin_pow(float x, int k) {
+  if constexpr (KS >= 0) {
+#pragma unroll
+    for (int i = 0; i < KS; i++) x *= x;
+    return x;
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < k; i++) x *= x;
+    return x;
+  }
 }
 
 // Blinn-Phong of one surface point: ambient + headlight (at the camera) + directional lights; V = unit vector to the camera
-__device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, const float* V, int mat, float* rgb) {
+template <int KS> __device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, const float* V, int mat, float* rgb) {
   float dif[3] = {P.ambient[0], P.ambient[1], P.ambient[2]}, spc[3] = {0, 0, 0};
   const float nv = fmaxf(rdot(N, V), 0.0f);
   for (int c = 0; c < 3; c++) dif[c] += P.head_diffuse[c] * nv;
   if (nv > P.spec_cut) {   // warp-coherent in practice: highlights are compact blobs
-    const float s = shin_pow(nv, P.shin_squarings);
+    const float s = shin_pow<KS>(nv, P.shin_squarings);
     for (int c = 0; c < 3; c++) spc[c] += P.head_specular[c] * s;
   }
 #pragma unroll
@@ -216,7 +223,7 @@ __device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, c
         const float nh = rdot(N, Hh);
         for (int c = 0; c < 3; c++) dif[c] += P.ldiffuse[l][c] * nl;
         if (nh > P.spec_cut) {
-          const float sh = shin_pow(nh, P.shin_squarings);
+          const float sh = shin_pow<KS>(nh, P.shin_squarings);
           for (int c = 0; c < 3; c++) spc[c] += P.lspecular[l][c] * sh;
         }
       }
@@ -230,23 +237,20 @@ __device__ __forceinline__ void shade(const KmRenderParams& P, const float* N, c
 // plane) and the half vector needs no normalisation of its own: |L + V|^2 = 2 + 2 L.V for unit L and V, hence
 // N.H = (L_z + V_z) rsqrt(2 + 2 L.V).  About a third of the instructions of shade(); rounding differs from it by an ulp
 // here and there (one grey level at most).
-__device__ __forceinline__ void shade_table(const KmRenderParams& P, const float* d, const float* tdif, unsigned lmask, float* rgb) {
+template <int KS> __device__ __forceinline__ void shade_table(const KmRenderParams& P, const float* d, const float* tdif, unsigned lmask, float* rgb) {
   const float vz = -d[2], nv = fmaxf(vz, 0.0f);
-  float dif[3] = {tdif[0], tdif[1], tdif[2]}, spc[3] = {0, 0, 0};
+  float dif[3] = {tdif[0], tdif[1], tdif[2]}, spc[3];
   for (int c = 0; c < 3; c++) dif[c] += P.head_diffuse[c] * nv;
-  if (nv > P.spec_cut) {
-    const float s = shin_pow(nv, P.shin_squarings);
-    for (int c = 0; c < 3; c++) spc[c] += P.head_specular[c] * s;
-  }
+  // highlights without branches (on the table they are on for most pixels): a select instead of divergence bookkeeping
+  const float s = nv > P.spec_cut ? shin_pow<KS>(nv, P.shin_squarings) : 0.0f;
+  for (int c = 0; c < 3; c++) spc[c] = P.head_specular[c] * s;
 #pragma unroll
   for (int l = 0; l < 4; l++) {
-    if ((lmask >> l) & 1u) {
-      const float lv = -rdot(P.ldir[l], d);
-      const float nh = (P.ldir[l][2] + vz) * rsqrtf(fmaxf(2.0f + 2.0f * lv, 1e-12f));
-      if (nh > P.spec_cut) {
-        const float sh = shin_pow(nh, P.shin_squarings);
-        for (int c = 0; c < 3; c++) spc[c] += P.lspecular[l][c] * sh;
-      }
+    if ((lmask >> l) & 1u) {   // warp-uniform
+      const float lv = rdot(P.ldir[l], d);
+      const float nh = (P.ldir[l][2] + vz) * rsqrtf(fmaxf(2.0f - 2.0f * lv, 1e-12f));
+      const float sh = nh > P.spec_cut ? shin_pow<KS>(nh, P.shin_squarings) : 0.0f;
+      for (int c = 0; c < 3; c++) spc[c] += P.lspecular[l][c] * sh;
     }
   }
   for (int c = 0; c < 3; c++) rgb[c] = fminf(P.mat[KM_MAT_TABLE][c] * dif[c] + P.mat_specular * spc[c], 1.0f);
@@ -257,7 +261,7 @@ __device__ __forceinline__ void shade_table(const KmRenderParams& P, const float
 // launch or the env only (camera axes, light terms of the table plane) is formed once per thread.  Tiles that see no
 // primitive (most of them) take a loop that knows only the table plane and the background.
 constexpr int KM_RENDER_THREADS = 128, KM_RENDER_ROWS = KM_RENDER_TILE * KM_RENDER_TILE / KM_RENDER_THREADS;
-__global__ void __launch_bounds__(KM_RENDER_THREADS) k_render_pixels(const float* __restrict__ recs, unsigned char* __restrict__ out, KmRenderParams P, int env0) {
+template <int KS> __global__ void __launch_bounds__(KM_RENDER_THREADS) k_render_pixels(const float* __restrict__ recs, unsigned char* __restrict__ out, KmRenderParams P, int env0) {
   __shared__ float rec[KM_REC_HDR + KM_PRIM_FLOATS * KM_RENDER_MAXPRIM];
   __shared__ unsigned s_mask;
   __shared__ __align__(16) unsigned char tile[KM_RENDER_TILE * KM_RENDER_TILE * 3];
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(KM_RENDER_THREADS) k_render_pixels(const float
         const float dy = -((float)py + 0.5f - 0.5f * (float)P.H) * inv;
         float d[3] = {base[0] + ay[0] * dy, base[1] + ay[1] * dy, base[2] + ay[2] * dy};
         rnorm(d);
-        if (above && d[2] < 0.0f) shade_table(P, d, tdif, lmask, rgb);
+        if (above && d[2] < 0.0f) shade_table<KS>(P, d, tdif, lmask, rgb);
       }
       unsigned char* t = tile + ly * (KM_RENDER_TILE * 3) + lx * 3;
       for (int c = 0; c < 3; c++) t[c] = (unsigned char)(int)(rgb[c] * 255.0f + 0.5f);
@@ -352,10 +356,10 @@ __global__ void __launch_bounds__(KM_RENDER_THREADS) k_render_pixels(const float
           const int pi = __ffs(mm) - 1;
           hit_prim(rec + KM_REC_HDR + KM_PRIM_FLOATS * pi, o, d, tbest, nrm, mat);
         }
-        if (mat == KM_MAT_TABLE) shade_table(P, d, tdif, lmask, rgb);
+        if (mat == KM_MAT_TABLE) shade_table<KS>(P, d, tdif, lmask, rgb);
         else if (mat >= 0) {
           const float V[3] = {-d[0], -d[1], -d[2]};
-          shade(P, nrm, V, mat, rgb);
+          shade<KS>(P, nrm, V, mat, rgb);
         }
       }
       unsigned char* t = tile + ly * (KM_RENDER_TILE * 3) + lx * 3;
