@@ -328,6 +328,9 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
     int* key = e.c.efc_state;
     const bool rebuild = __any_sync(FULL, (iscube && hd != hd_cached) || (unsigned)key[0] != pm || (unsigned)key[1] != nm);
     if (refactor || rebuild) g.sync();
+#ifdef KM_PHASE_CLOCKS
+    if (lane == 0) { e.clk[14] += rebuild ? 1u : 0u; e.clk[15] += refactor ? 1u : 0u; }   // profiling build: event counts
+#endif
     if (rebuild) {
     if (lane == 0) { key[0] = (int)pm; key[1] = (int)nm; }
     // cube block: diag + sum over contacts of Jq^T W Jq, one lower-triangle entry (ei, ej) per lane
@@ -544,6 +547,9 @@ template <class S, typename T, class E, bool CPL> struct WarpSolver {
       qacc += alpha * search; Ma += alpha * Mv;
       sfor<0, NS>([&](auto Sx) { constexpr int s = decltype(Sx)::value; jar[s] += alpha * jv[s]; });
       niter++;
+#ifdef KM_PHASE_CLOCKS
+      if (lane == 0) e.clk[9] += 1u;   // CLK_SOL_VOTE slot (unused by this solver): Newton iterations of the env step
+#endif
     }
     if (isdof) { e.qacc[lane] = qacc; e.warm[lane] = qacc; }
     if (lane == 0) { e.solver_niter = niter; e.ls_evals += evals; }

@@ -35,7 +35,7 @@ for t in range(40):
         tp = torch.cat([tot, tot.new_zeros(pad)]).view(ncta, epb_).max(1).values
         q = torch.quantile(tp, torch.tensor([0.1, 0.5, 0.9, 0.99, 1.0], dtype=tp.dtype))
         print("   per-CTA total cycles p10/p50/p90/p99/max: " + " ".join(f"{x:.0f}" for x in q.tolist()))
-        busy = c[:, :11].sum(1) + c[:, 12] + c[:, 13]          # everything but the barrier waits
+        busy = c[:, :9].sum(1) + c[:, 10] + c[:, 12] + c[:, 13]          # everything but the barrier waits
         bq = torch.quantile(busy, torch.tensor([0.1, 0.5, 0.9, 0.99, 1.0], dtype=tp.dtype))
         print("   per-env busy cycles (no barrier waits) p10/p50/p90/p99/max: " + " ".join(f"{x:.0f}" for x in bq.tolist()))
         bf = torch.quantile(c[:, 12], torch.tensor([0.1, 0.5, 0.9, 0.99, 1.0], dtype=tp.dtype))
@@ -43,4 +43,5 @@ for t in range(40):
         top = torch.argsort(busy, descending=True)[:6]
         fl = sim.con_flags.cpu(); nc = sim.ncon.cpu()
         for i in top.tolist():
-            print(f"     env {i} (cta {i // epb_}) busy {busy[i]:.0f} ncon {int(nc[i])} flags {int(fl[i])} | " + " ".join(f"{nm} {c[i, k]:.0f}" for k, nm in enumerate(names)))
+            print(f"     env {i} (cta {i // epb_}) busy {busy[i]:.0f} ncon {int(nc[i])} flags {int(fl[i])} | " + " ".join(f"{nm} {c[i, k]:.0f}" for k, nm in enumerate(names)) + f" | newton its {c[i, 9]:.0f} cube rebuilds {c[i, 14]:.0f} chain refactors {c[i, 15]:.0f}")
+        print(f"   batch means: newton iterations {c[:, 9].mean():.1f}, cube-block rebuilds {c[:, 14].mean():.1f}, chain-block refactors {c[:, 15].mean():.1f} per env step")
