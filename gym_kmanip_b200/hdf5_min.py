@@ -3,7 +3,9 @@
 The reference logs episodes with h5py (reference gym_kmanip/log_h5py.py:13-61: groups, float32 / uint8 datasets, scalar and
 list attributes).  This module writes the same tree in the oldest, most widely readable layout of the HDF5 File Format
 Specification (version 0 superblock, version 1 object headers, symbol-table groups = v1 B-tree + local heap + one symbol
-node per group, contiguous datasets, version 1 attribute messages), which every libhdf5 / h5py reads:
+node per group, contiguous datasets, version 1 attribute messages) -- the layout every libhdf5 release understands.  The
+build image has neither h5py nor libhdf5, so here the files are checked by the reader below and by byte-level tests of
+the structures the specification prescribes (tests/test_hdf5_min.py); the h5py read-back test runs wherever h5py imports:
 
     write(path, {"action": ndarray, "observations": {"qpos": ndarray, "images": {}}, "metadata": {}},
           attrs={"": {"sim": True}, "metadata": {"q_len": 9, "name": "KManipSoloArm"}})
