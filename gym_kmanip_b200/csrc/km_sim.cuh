@@ -1206,6 +1206,65 @@ template <class S, typename T, int G, class E, class B> KM_HD void ik_chain_fk(E
   q2mat(b.smat, sq);
 }
 
+// The same with one chain link per lane (warp-per-env kernels; every lane of the group calls it): each lane forms its
+// link's transform relative to the parent (the fp64 sincos and quaternion products of all links at once), an inclusive
+// prefix product over the chain composes them in four rounds of shuffles, and the quaternion is normalised once at the
+// end instead of after every link -- results differ from the serial sweep by a few ulp of fp64.
+template <class S, typename T, int G, class E, class B> KM_HD void ik_chain_fk_lanes(E& e, B& b, const Model<S, T>& m, const Grp<G>& g, int a, const double* x) {
+  typedef Num<double> N;
+  static_assert(Dim<S>::MAXLEVEL <= 16 && G >= Dim<S>::MAXLEVEL, "one chain link per lane, four prefix rounds");
+  const int nc = m.arm_nchain[a];
+  const bool on = g.lane < nc;
+  const int k = on ? g.lane : nc - 1;            // surplus lanes shadow the last link (they take part in the shuffles)
+  const int l = m.arm_chain[a][k], mi = m.arm_chain_mask[a][k];
+  const double th = mi >= 0 ? x[mi] : (double)e.qpos[l];
+  const bool hinge = m.jtype[l] == JT_HINGE;
+  double q[4] = {m.dk_lquat[l][0], m.dk_lquat[l][1], m.dk_lquat[l][2], m.dk_lquat[l][3]};
+  double p[3] = {m.dk_lpos[l][0], m.dk_lpos[l][1], m.dk_lpos[l][2]};
+  if (hinge) {                                     // q <- q * (c, 0, 0, s)
+    double sn, cs;
+    N::sincos(th * 0.5, &sn, &cs);
+    const double t0 = q[0] * cs - q[3] * sn, t1 = q[1] * cs + q[2] * sn, t2 = q[2] * cs - q[1] * sn, t3 = q[3] * cs + q[0] * sn;
+    q[0] = t0; q[1] = t1; q[2] = t2; q[3] = t3;
+  } else {                                         // slide along the link's own z: the offset belongs to the link's frame origin
+    const double z[3] = {0, 0, th};
+    double d[3];
+    qrot(d, q, z);
+    p[0] += d[0]; p[1] += d[1]; p[2] += d[2];
+  }
+#pragma unroll
+  for (int d = 1; d < 16; d *= 2) {
+    const bool has = g.lane >= d && on;
+    const int src = has ? g.lane - d : g.lane;
+    double qa[4], pa[3];
+    for (int i = 0; i < 4; i++) qa[i] = g.shfl(q[i], src);
+    for (int i = 0; i < 3; i++) pa[i] = g.shfl(p[i], src);
+    if (has) {
+      double t[3], qq[4];
+      qrot(t, qa, p);
+      p[0] = pa[0] + t[0]; p[1] = pa[1] + t[1]; p[2] = pa[2] + t[2];
+      qmul(qq, qa, q);
+      q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+    }
+  }
+  qnormalize(q);
+  double mat[9];
+  q2mat(mat, q);
+  if (on) {
+    // anchor = the joint's position: the frame origin, minus the slide offset for sliders
+    const double off = hinge ? 0.0 : th;
+    for (int i = 0; i < 3; i++) { b.ax[k][i] = mat[3 * i + 2]; b.an[k][i] = p[i] - mat[3 * i + 2] * off; }
+  }
+  if (g.lane == nc - 1) {
+    double t[3], sq[4];
+    mulv3(t, mat, m.dk_site_pos[a]);
+    for (int i = 0; i < 3; i++) b.spos[i] = p[i] + t[i];
+    qmul(sq, q, m.dk_site_quat[a]);
+    q2mat(b.smat, sq);
+  }
+  g.sync();
+}
+
 // ik_res (reference ik_mujoco.py:20-53) from the chain pose currently in e.b; pose rows by lane 0, regularisers by all
 template <class S, typename T, int G, class E, class B> KM_HD void ik_residual(E& e, B& b, const Model<S, T>& m, const Grp<G>& g, int a, const double* x, double* res) {
   const int n = m.arm_nmask[a];
@@ -1285,10 +1344,17 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
   }
   const bool feasible = !g.any(bad);
   g.sync();
+  // chain kinematics: one link per lane in the warp-per-env kernels, one lane sweeping the chain otherwise
+#if KM_WARP_CODE
+  constexpr bool kFkLanes = G >= D::MAXLEVEL && G > 1;
+#else
+  constexpr bool kFkLanes = false;
+#endif
+  if constexpr (kFkLanes) ik_chain_fk_lanes<S, T, G>(e, b, m, g, a, b.x);
   if (g.lane == 0) {
     // goal = current site pose displaced by the action (EE_POS_DELTA 0.01, EE_ORN_DELTA 0.1, extrinsic xyz Euler)
     double eul[3];
-    ik_chain_fk<S, T, G>(e, b, m, a, b.x);
+    if constexpr (!kFkLanes) ik_chain_fk<S, T, G>(e, b, m, a, b.x);
     for (int i = 0; i < 3; i++) b.goal[i] = (double)act[m.off_pos[a] + i] * 0.01 + b.spos[i];
     mat_to_euler_xyz_ext(eul, b.smat);
     for (int i = 0; i < 3; i++) eul[i] = (double)act[m.off_orn[a] + i] * 0.1 + eul[i];
@@ -1370,9 +1436,10 @@ KM_TPL KM_FN void ik_solve(KM_ARGS, int a, const float* act) {
         for (int i = 0; i < n; i++) { double t = b.gv[i]; for (int k = 0; k < i; k++) t -= b.A[i][k] * b.gv[k]; b.gv[i] = t / b.A[i][i]; }
         for (int i = n - 1; i >= 0; i--) { double t = b.gv[i]; for (int k = i + 1; k < n; k++) t -= b.A[k][i] * b.gv[k]; b.gv[i] = t / b.A[i][i]; }
         for (int i = 0; i < n; i++) b.xn[i] = tclip(b.x[i] + b.gv[i], b.lo[i], b.hi[i]);
-        ik_chain_fk<S, T, G>(e, b, m, a, b.xn);
+        if constexpr (!kFkLanes) ik_chain_fk<S, T, G>(e, b, m, a, b.xn);
       }
       g.sync();
+      if constexpr (kFkLanes) ik_chain_fk_lanes<S, T, G>(e, b, m, g, a, b.xn);
       ik_residual<S, T, G>(e, b, m, g, a, b.xn, b.rn);
       double cn = 0;
       KM_FOR(k, nr) cn += 0.5 * b.rn[k] * b.rn[k];
