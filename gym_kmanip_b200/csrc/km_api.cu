@@ -31,7 +31,7 @@ struct km_sim {
   void* d_model;
   void* d_state;
   int *d_step, *d_episode, *d_niter, *d_ls;
-  int *d_order, *d_tile_counter;   // cost-ordered walk of the step kernels (order_envs)
+  int *d_order, *d_tile_counter, *d_cost;   // cost-ordered walk of the step kernels (order_envs)
   int order_mode;   // -1 = automatic (on when the lane-group mapping walks more tiles than CTAs), 0 = off, 1 = on
   unsigned* d_clk;   // caller-owned buffer of km_debug_phase_clocks (debug builds)
   void* d_ep_return;  // running return of every env (dtype of the handle)
@@ -156,7 +156,7 @@ static KmArgs base_args(km_sim* h, void* stream) {
   KmArgs a;
   std::memset(&a, 0, sizeof(a));
   a.model = h->d_model; a.state = h->d_state; a.step = h->d_step; a.episode = h->d_episode;
-  a.niter = h->d_niter; a.ls = h->d_ls; a.clk = h->d_clk;
+  a.niter = h->d_niter; a.ls = h->d_ls; a.cost = h->d_cost; a.clk = h->d_clk;
   a.ep_return = h->d_ep_return; a.totals = h->d_totals;
   a.n = h->n; a.seed = h->seed; a.env0 = h->env0; a.G = h->G; a.epb = h->epb; a.grid = h->grid; a.lpw = h->lpw > 0 ? h->lpw : 32; a.tpl_small_regs = h->tpl_ctas > 1;
   a.trf_bytes = h->ik_mode == 1 ? (int)sizeof(km::trf::TrfWork) : 0;
@@ -280,6 +280,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
   KM_ALLOC(h->d_niter, n * sizeof(int));
   KM_ALLOC(h->d_ls, n * sizeof(int));
   KM_ALLOC(h->d_order, n * sizeof(int));
+  KM_ALLOC(h->d_cost, n * sizeof(int));
   KM_ALLOC(h->d_tile_counter, sizeof(int));
   KM_ALLOC(h->d_act, n * task->act_dim * sizeof(float));
   KM_ALLOC(h->d_obs, n * h->vt.obs_dim * sb);
@@ -297,6 +298,7 @@ int km_create(const km_model* model, const km_task* task, int scene, int n_envs,
       (e = cudaMemset(h->d_niter, 0, n * sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->d_ep_return, 0, n * sb)) != cudaSuccess ||
       (e = cudaMemset(h->d_totals, 0, 4 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMemset(h->d_cost, 0, n * sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->d_ls, 0, n * sizeof(int))) != cudaSuccess) {
     km_destroy(h);
     return cuda_fail(e, "km_create: initialisation");
@@ -328,7 +330,7 @@ void km_destroy(km_handle h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   void* ptrs[] = {h->d_model, h->d_state, h->d_step, h->d_episode, h->d_niter, h->d_ls, h->d_act, h->d_obs, h->d_reward,
-                  h->d_xyz, h->d_trunc, h->d_mask, h->d_recs, h->d_rgb, h->d_ep_return, h->d_totals, h->d_order, h->d_tile_counter};
+                  h->d_xyz, h->d_trunc, h->d_mask, h->d_recs, h->d_rgb, h->d_ep_return, h->d_totals, h->d_order, h->d_tile_counter, h->d_cost};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -392,7 +394,8 @@ int km_step(km_handle h, const float* action_dev, const km_step_out* out, int au
   }
   const long tiles_ = ((long)h->n + h->epb - 1) / h->epb;
   if (h->order_mode == 1 || (h->order_mode < 0 && h->G >= 16 && tiles_ > h->grid)) {
-    k_order_envs<<<1, 1024, 0, a.stream>>>(h->d_ls, h->n, 1, h->d_order, h->d_tile_counter);
+    // 256 buckets: two line-search evaluations wide, or (exact-parity IK, whose evaluations weigh 64) an eighth of an IK evaluation
+    k_order_envs<<<1, 1024, 0, a.stream>>>(h->d_cost, h->n, h->ik_mode == 1 ? 3 : 1, h->d_order, h->d_tile_counter);
     KM_CUDA(cudaGetLastError());
     a.order = h->d_order; a.tile_counter = h->d_tile_counter;
     h->launches++;

@@ -429,6 +429,7 @@ template <class S, typename T, class E, class B> KM_HD void ik_trf_serial(E& e, 
     }
   }
   for (int i = 0; i < n; i++) b.x[i] = x[i];
+  e.ik_evals += nfev;
 }
 
 }  // namespace km

@@ -46,6 +46,7 @@ struct KmArgs {
   // fetch (CTAs take the next tile when they finish one: longest tiles first, balanced finish).  Both may be null.
   const int* order;
   int* tile_counter;
+  int* cost;       // ordering key of the next step: line-search evaluations + 64 x IK function evaluations of this one
   int trf_bytes;   // extra dynamic shared memory per env: work arrays of the exact-parity IK (ik_mode = 1), else 0
   int lpw;   // thread-per-env (local) mapping: active lanes per warp (envs of a CTA are spread over its warps)
   int tpl_small_regs;   // thread-per-env (local): use the 128-register instantiation even for CTAs of <= 256 threads (several CTAs per SM)
@@ -157,6 +158,7 @@ template <class S, typename T, int G> __global__ void __launch_bounds__(max_thre
       if (g.lane == 0) {
         if (a.niter) a.niter[envc] = e.solver_niter;
         if (a.ls) a.ls[envc] = e.ls_evals;
+        if (a.cost) a.cost[envc] = e.ls_evals + 64 * e.ik_evals;
       }
     }
     g.sync();
@@ -226,6 +228,7 @@ template <class S, typename T, bool LOCAL, int MAXT = 256> __global__ void __lau
         store_state<S, T, 1>(e, a, envc, g);
         if (a.niter) a.niter[envc] = e.solver_niter;
         if (a.ls) a.ls[envc] = e.ls_evals;
+        if (a.cost) a.cost[envc] = e.ls_evals;
       }
       if (a.tile_counter) {
         __syncthreads();

@@ -142,6 +142,7 @@ template <class S, typename T, bool TPE_ = false> struct Env {
   T bias[D::NV], qfrc_smooth[D::NV], qacc_smooth[D::NV], qacc[D::NV];
   T obs[D::OBS];
   int solver_niter, ls_evals;                     // diagnostics of the last sub-step
+  int ik_evals;                                   // exact-parity IK: function evaluations of this env step (ordering key)
 #ifdef KM_PHASE_CLOCKS
   unsigned clk[16], clk_last;                     // debug build: cycles per phase of the current env step (KM_CLK)
 #endif

@@ -1578,7 +1578,7 @@ KM_TPL KM_FN void init_env(KM_ARGS) {
     e.efc_desc[r] = efc_pack(EFC_FRICTION, m.fric_dof[r], 0, 0);
     e.efc_D[r] = m.fr_D[r];
   }
-  if (g.lane == 0) { e.ls_evals = 0; e.solver_niter = 0; e.ncon = 0; e.nlim = 0; e.nefc = D::NFRIC; }
+  if (g.lane == 0) { e.ls_evals = 0; e.ik_evals = 0; e.solver_niter = 0; e.ncon = 0; e.nlim = 0; e.nefc = D::NFRIC; }
   g.sync();
 }
 
