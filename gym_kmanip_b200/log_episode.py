@@ -8,7 +8,10 @@ a_len columns (log_h5py.py:55; a_len is the number of action keys, env_base.py:1
 
 h5py is not part of the build image: when it imports, ``episode_<k>.hdf5`` is written exactly as the reference does;
 otherwise the same tree is written as ``episode_<k>.hdf5`` by the minimal pure-Python writer ``hdf5_min.py``
-(fixed-length string / numeric attributes; bools as uint8).  Camera datasets of the Vision ids are not logged.
+(fixed-length string / numeric attributes; bools as uint8).  The Vision ids also log their camera observations
+(``observations/images/<cam.name>``, ``metadata/<cam.log_name>``: resolution, focal_length, principal_point) -- single-env
+class only; the batched logger keeps to the joint-space datasets.  Files are written when the episode ends (the reference
+flushes every step).
 """
 from __future__ import annotations
 
@@ -46,6 +49,10 @@ class EpisodeLog:
         self.qpos = np.zeros((K.MAX_EPISODE_STEPS, self.q_len), dtype=np.float32)
         self.qvel = np.zeros((K.MAX_EPISODE_STEPS, self.q_len), dtype=np.float32)
         self.action = np.zeros((K.MAX_EPISODE_STEPS, self.a_len), dtype=np.float32)
+        # camera observations of the Vision ids (reference log_h5py.py:36-46 `cam`, env_base.py:231-234): one uint8 dataset
+        # per camera under observations/images/<cam.name> and its intrinsics as attributes of metadata/<cam.log_name>
+        self.cams = list(info.get("cameras") or [])
+        self.images = {c.name: np.zeros((K.MAX_EPISODE_STEPS, c.h, c.w, c.c), dtype=c.dtype) for c in self.cams}
         self.path = None
 
     def step(self, action: Dict[str, np.ndarray], observation: Dict[str, np.ndarray], info: Dict[str, Any]) -> None:
@@ -53,6 +60,11 @@ class EpisodeLog:
         self.action[i] = action["grip_r"]                 # broadcast over a_len columns, as in the reference
         self.qpos[i] = observation["q_pos"]
         self.qvel[i] = observation["q_vel"]
+        for c in self.cams:                                # log_h5py.py:59-60
+            self.images[c.name][i] = observation[c.log_name]
+
+    def _cam_attrs(self, c) -> Dict[str, Any]:
+        return {"resolution": [c.w, c.h], "focal_length": c.fl, "principal_point": list(c.pp)}
 
     def end(self) -> str:
         if HAVE_H5PY:                                      # pragma: no cover
@@ -66,6 +78,11 @@ class EpisodeLog:
                     except TypeError:
                         pass
                 f.create_group("observations/images")
+                for c in self.cams:
+                    gc = f.create_group(f"metadata/{c.log_name}")
+                    for key, value in self._cam_attrs(c).items():
+                        gc.attrs[key] = value
+                    f.create_dataset(f"/observations/images/{c.name}", data=self.images[c.name], chunks=(1, c.h, c.w, c.c))
                 f.create_dataset("observations/qpos", data=self.qpos)
                 f.create_dataset("observations/qvel", data=self.qvel)
                 f.create_dataset("action", data=self.action)
@@ -81,22 +98,38 @@ class EpisodeLog:
                     meta[key] = value
                 except (TypeError, ValueError):
                     pass               # "Could not save ..." in the reference (log_h5py.py:21-24)
-            hdf5_min.write(self.path, {"action": self.action, "metadata": {},
-                                       "observations": {"images": {}, "qpos": self.qpos, "qvel": self.qvel}},
-                           attrs={"": {"sim": self.attrs["sim"]}, "metadata": meta})
+            attrs = {"": {"sim": self.attrs["sim"]}, "metadata": meta}
+            mtree: Dict[str, Any] = {}
+            for c in self.cams:                            # metadata/<cam.log_name>: "camera/head" nests a group per component
+                node, path = mtree, "metadata"
+                for part in c.log_name.split("/"):
+                    node = node.setdefault(part, {})
+                    path += "/" + part
+                attrs[path] = self._cam_attrs(c)
+            hdf5_min.write(self.path, {"action": self.action, "metadata": mtree,
+                                       "observations": {"images": {c.name: self.images[c.name] for c in self.cams},
+                                                        "qpos": self.qpos, "qvel": self.qvel}}, attrs=attrs)
         return self.path
 
 
-def read_episode(path: str):
-    """Reads an episode file written by this module: (qpos, qvel, action, root attrs, metadata attrs).  Uses h5py when it
-    imports, else the reader of hdf5_min (which parses exactly the subset of HDF5 that hdf5_min writes)."""
+def read_episode(path: str, with_images: bool = False):
+    """Reads an episode file written by this module: (qpos, qvel, action, root attrs, metadata attrs) and, with
+    ``with_images``, two more items: {camera name: images}, {camera log name: intrinsics}.  Uses h5py when it imports, else
+    the reader of hdf5_min (which parses exactly the subset of HDF5 that hdf5_min writes)."""
     if HAVE_H5PY:                                          # pragma: no cover
         with h5py.File(path, "r") as f:
-            return (f["observations/qpos"][:], f["observations/qvel"][:], f["action"][:], dict(f.attrs), dict(f["metadata"].attrs))
+            out = (f["observations/qpos"][:], f["observations/qvel"][:], f["action"][:], dict(f.attrs), dict(f["metadata"].attrs))
+            if with_images:
+                cams = {}
+                f["metadata"].visititems(lambda nm, o: cams.__setitem__(nm, dict(o.attrs)) if len(o.attrs) else None)
+                out += ({k: v[:] for k, v in f["observations/images"].items()}, cams)
+            return out
     from . import hdf5_min
     tree, attrs = hdf5_min.read(path)
-    assert tree["observations"]["images"] == {}
-    return tree["observations"]["qpos"], tree["observations"]["qvel"], tree["action"], attrs.get("", {}), attrs.get("metadata", {})
+    out = (tree["observations"]["qpos"], tree["observations"]["qvel"], tree["action"], attrs.get("", {}), attrs.get("metadata", {}))
+    if with_images:
+        out += (tree["observations"]["images"], {k[len("metadata/"):]: v for k, v in attrs.items() if k.startswith("metadata/")})
+    return out
 
 
 def new(log_dir: str, info: Dict[str, Any]) -> EpisodeLog:
@@ -161,6 +194,7 @@ class BatchEpisodeLog:
             meta = dict(self.info, env=gid, episode=self.episode[c], step=int(rows[k]), q_len=self.q_len, a_len=self.a_len, sim=True)
             f = EpisodeLog.__new__(EpisodeLog)
             f.q_len, f.a_len, f.attrs, f.path = self.q_len, self.a_len, {"sim": True}, None
+            f.cams, f.images = [], {}
             f.stem = os.path.join(self.log_dir, f"env{gid:06d}_episode_{self.episode[c]}")
             f.metadata = {key: v for key, v in meta.items() if _jsonable(v)}
             f.qpos, f.qvel = qpos[:, k], qvel[:, k]

@@ -247,6 +247,32 @@ def test_single_env_episode_logging(tmp_path, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_single_env_episode_logging_with_cameras(tmp_path, monkeypatch):
+    """Vision id with log_h5py=True: the episode file carries the camera observations and intrinsics
+    (reference log_h5py.py:36-46, 59-60; env_base.py:231-234)."""
+    from gym_kmanip_b200 import constants as K
+    from gym_kmanip_b200.log_episode import read_episode
+    monkeypatch.setattr(K, "DATA_DIR", str(tmp_path))
+    env = k.make("KManipSoloArmVision", log_h5py=True, ik_mode=0)
+    u = env.unwrapped
+    u.action_space.seed(0)
+    obs0, _ = env.reset()
+    seen = []
+    for _ in range(3):
+        obs, *_ = env.step(u.action_space.sample())
+        seen.append(obs)
+    env.close()
+    files = sorted(os.listdir(u.log_dir))
+    assert files == ["episode_1.hdf5"]
+    qpos, qvel, action, attrs, meta, images, cam_meta = read_episode(os.path.join(u.log_dir, files[0]), with_images=True)
+    assert sorted(images) == ["grip_r", "head"] and images["head"].shape == (64, 480, 640, 3) and images["grip_r"].shape == (64, 40, 60, 3)
+    for t, obs in enumerate(seen):
+        assert np.array_equal(images["head"][t], obs["camera/head"]) and np.array_equal(images["grip_r"][t], obs["camera/grip_r"])
+    assert images["head"][:3].any() and not images["head"][3:].any()
+    assert list(cam_meta["camera/head"]["resolution"]) == [640, 480] and cam_meta["camera/head"]["focal_length"] == 448
+
+
+@pytest.mark.gpu
 def test_vector_env_episode_logging_from_device_ring_buffers(tmp_path):
     """KManipVectorEnv(log_dir=...): logged envs' rows stay on the device until truncation, then one file per episode."""
     import torch

@@ -149,3 +149,28 @@ def test_batch_episode_log_ring_buffers(tmp_path):
         assert np.all(action[r] == act[4, 6].numpy())
     assert not qpos[T:].any() and not action[T:].any()
     assert int(log.row[0]) == 1 and log.qpos[1:].abs().sum() == 0   # the ninth step opened episode 3
+
+
+def test_episode_log_with_cameras(tmp_path):
+    """Vision ids: per-camera image datasets and intrinsics in the episode file (reference log_h5py.py:36-46, 59-60)."""
+    from gym_kmanip_b200 import constants as K, log_episode
+    cams = [K.CAMERAS["grip_r"], K.CAMERAS["grip_l"]]
+    info = {"episode": 7, "sim": True, "q_len": 10, "a_len": 3, "step": 0, "cameras": cams}
+    f = log_episode.new(str(tmp_path), info)
+    rng = np.random.default_rng(2)
+    frames = []
+    for t in range(1, 4):
+        info["step"] = t
+        obs = {"q_pos": rng.uniform(0, 1, 10), "q_vel": rng.uniform(-1, 1, 10)}
+        for c in cams:
+            obs[c.log_name] = rng.integers(0, 256, (c.h, c.w, c.c), dtype=np.uint8)
+        log_episode.step(f, {"grip_r": np.float32([0.5])}, obs, info)
+        frames.append(obs)
+    path = log_episode.end(f)
+    qpos, qvel, action, attrs, meta, images, cam_meta = log_episode.read_episode(path, with_images=True)
+    assert sorted(images) == ["grip_l", "grip_r"] and images["grip_r"].shape == (64, 40, 60, 3) and images["grip_r"].dtype == np.uint8
+    for t, obs in enumerate(frames):
+        assert np.array_equal(images["grip_r"][t], obs["camera/grip_r"]) and np.array_equal(images["grip_l"][t], obs["camera/grip_l"])
+    assert not images["grip_r"][3:].any()
+    assert list(cam_meta["camera/grip_r"]["resolution"]) == [60, 40] and cam_meta["camera/grip_r"]["focal_length"] == 45
+    assert list(cam_meta["camera/grip_l"]["principal_point"]) == [30, 20] and "cameras" not in meta and meta["episode"] == 7
